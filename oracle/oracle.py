@@ -1,0 +1,154 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes access to the CPU restatement (oracle/nbody_oracle.c -> liboracle.so) and
+to the compiled, unmodified reference (oracle/_ref/, built by oracle/Makefile from
+/root/reference).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module; the product path
+(nbody-demo-2023_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+REF_DIR = os.path.join(HERE, "_ref")
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def build(with_ref: bool = True) -> None:
+    """Compile liboracle.so (always) and oracle/_ref (only where /root/reference exists)."""
+    targets = ["all"] + (["ref"] if with_ref else [])
+    subprocess.run(["make", "-s", "-C", HERE] + targets, check=True)
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build(with_ref=False)
+        L = C.CDLL(LIB_PATH)
+        L.oracle_ic_uniform.argtypes = [C.c_int] + [_f32p] * 7
+        L.oracle_ic_uniform.restype = None
+        for name in ("oracle_run_ver2", "oracle_run_ver0", "oracle_run_ver7"):
+            fn = getattr(L, name)
+            fn.argtypes = [C.c_int] + [_f32p] * 7 + [C.c_float, C.c_int, _f32p]
+            fn.restype = C.c_int
+        L.oracle_acc_fp64.argtypes = [C.c_int] + [_f32p] * 4 + [C.c_int, _i32p] + [_f64p] * 3
+        L.oracle_acc_fp64.restype = None
+        L.oracle_kenergy_fp64.argtypes = [C.c_int] + [_f32p] * 4
+        L.oracle_kenergy_fp64.restype = C.c_double
+        L.oracle_gflop_per_step.argtypes = [C.c_int]
+        L.oracle_gflop_per_step.restype = C.c_double
+        L.oracle_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+class State:
+    """Host SoA particle state: px py pz vx vy vz mass (float32[n] each)."""
+
+    FIELDS = ("px", "py", "pz", "vx", "vy", "vz", "mass")
+
+    def __init__(self, n: int):
+        self.n = n
+        for f in self.FIELDS:
+            setattr(self, f, np.zeros(n, dtype=np.float32))
+
+    def arrays(self):
+        return [getattr(self, f) for f in self.FIELDS]
+
+    def copy(self) -> "State":
+        s = State(self.n)
+        for f in self.FIELDS:
+            setattr(s, f, getattr(self, f).copy())
+        return s
+
+    def pos(self) -> np.ndarray:
+        return np.stack([self.px, self.py, self.pz], axis=1)
+
+    def vel(self) -> np.ndarray:
+        return np.stack([self.vx, self.vy, self.vz], axis=1)
+
+
+def ic_uniform(n: int) -> State:
+    s = State(n)
+    lib().oracle_ic_uniform(n, *s.arrays())
+    return s
+
+
+def run(state: State, nsteps: int, dt: float = 0.1, variant: str = "ver2") -> np.ndarray:
+    """Advance `state` in place by nsteps; returns per-step kenergy (float32[nsteps])."""
+    ke = np.zeros(max(nsteps, 1), dtype=np.float32)
+    fn = getattr(lib(), "oracle_run_" + variant)
+    rc = fn(state.n, *state.arrays(), np.float32(dt), nsteps, ke)
+    if rc != 0:
+        raise MemoryError("oracle allocation failed")
+    return ke[:nsteps]
+
+
+def acc_fp64(state: State, sel: np.ndarray) -> np.ndarray:
+    sel = np.ascontiguousarray(sel, dtype=np.int32)
+    out = [np.zeros(sel.size, dtype=np.float64) for _ in range(3)]
+    lib().oracle_acc_fp64(state.n, state.px, state.py, state.pz, state.mass, sel.size, sel, *out)
+    return np.stack(out, axis=1)
+
+
+def kenergy_fp64(state: State) -> float:
+    return float(lib().oracle_kenergy_fp64(state.n, state.vx, state.vy, state.vz, state.mass))
+
+
+def gflop_per_step(n: int) -> float:
+    return float(lib().oracle_gflop_per_step(n))
+
+
+def num_threads() -> int:
+    return int(lib().oracle_num_threads())
+
+
+# ----------------------------------------------------------------------------
+#  compiled reference (oracle/_ref)
+# ----------------------------------------------------------------------------
+def ref_available(ver: str = "ver2") -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "ref_dump_" + ver))
+
+
+def read_dump(path: str):
+    with open(path, "rb") as f:
+        raw = f.read()
+    assert raw[:4] == b"NBXD", "bad dump magic"
+    n, steps = struct.unpack_from("<ii", raw, 4)
+    (ke,) = struct.unpack_from("<f", raw, 12)
+    (secs,) = struct.unpack_from("<d", raw, 16)
+    body = np.frombuffer(raw, dtype=np.float32, offset=24, count=7 * n).reshape(7, n)
+    s = State(n)
+    for k, f in enumerate(State.FIELDS):
+        setattr(s, f, body[k].copy())
+    return s, np.float32(ke), secs, steps
+
+
+def ref_run(ver: str, n: int, nsteps: int, threads: int | None = None):
+    """Run the compiled reference `ver` for nsteps; returns (State, kenergy_last, loop_seconds)."""
+    exe = os.path.join(REF_DIR, "ref_dump_" + ver)
+    env = dict(os.environ)
+    if threads is not None:
+        env["OMP_NUM_THREADS"] = str(threads)
+    env.setdefault("OMP_PROC_BIND", "close")
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "dump.bin")
+        subprocess.run([exe, str(n), str(nsteps), out], check=True, env=env,
+                       stdout=subprocess.DEVNULL)
+        s, ke, secs, _ = read_dump(out)
+    return s, ke, secs
