@@ -1,0 +1,803 @@
+// nbx.cu -- the C ABI of libnbx.so (include/nbx.h): context, device-resident state,
+// step launcher, multi-GPU exchange.  Host side of the kernels in nbx_kernels.cuh.
+//
+// Reference boundary this implements: the body of a backend's GSimulation::start()
+// (ver5_all/programming_models/cuda/Compute.cu:69-232) minus printing -- allocation
+// (:76-108), upload (:115-123), the per-step kernel + host update (:150-194).  Unlike
+// that backend nothing crosses PCIe per step and every CUDA/NCCL call is checked.
+#include "../../include/nbx.h"
+#include "ic.hpp"
+#include "nbx_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using nbx::StepParams;
+
+// ------------------------------------------------------------------------------
+//  errors
+// ------------------------------------------------------------------------------
+static thread_local std::string g_err = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(NBX_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------
+//  NCCL, loaded on first use so single-GPU users need no libnccl at all
+// ------------------------------------------------------------------------------
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load()
+{
+    if (g_nccl.handle) return NBX_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names) {
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(NBX_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                            \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                                     \
+    if (!g_nccl.field) return fail(NBX_ERR_NCCL, "libnccl lacks symbol %s", name);
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommInitAll, "ncclCommInitAll")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(AllGather, "ncclAllGather")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.handle = h;
+    return NBX_OK;
+}
+
+#define NC(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess)                                                                     \
+            return fail(NBX_ERR_NCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------
+//  kernel-shape table
+// ------------------------------------------------------------------------------
+struct Variant {
+    const char *name;
+    int r2, threads, tj, stages, unroll, minb;
+    int smem;
+    const void *fn;
+};
+
+template <int R2, int THREADS, int TJ, int STAGES, int UNROLL, int MINB>
+static Variant make_variant(const char *name)
+{
+    return Variant{name, R2, THREADS, TJ, STAGES, UNROLL, MINB, nbx::step_smem_bytes<THREADS, TJ, STAGES>(),
+                   (const void *)nbx::step_kernel<R2, THREADS, TJ, STAGES, UNROLL, MINB>};
+}
+
+static const std::vector<Variant> &variants()
+{
+    static const std::vector<Variant> v = {
+        make_variant<2, 256, 256, 4, 2, 2>("r4_t256_u2"),   // default
+        make_variant<2, 128, 256, 4, 2, 4>("r4_t128_u2"),
+        make_variant<2, 256, 256, 4, 4, 2>("r4_t256_u4"),
+        make_variant<2, 256, 256, 4, 1, 2>("r4_t256_u1"),
+        make_variant<3, 256, 256, 4, 2, 2>("r6_t256_u2"),
+        make_variant<3, 128, 256, 4, 2, 4>("r6_t128_u2"),
+        make_variant<4, 256, 256, 4, 1, 1>("r8_t256_u1"),
+        make_variant<4, 128, 256, 4, 1, 3>("r8_t128_u1"),
+        make_variant<1, 256, 256, 4, 4, 3>("r2_t256_u4"),
+        make_variant<1, 128, 256, 4, 4, 6>("r2_t128_u4"),
+        make_variant<2, 512, 512, 4, 2, 1>("r4_t512_u2"),
+        make_variant<2, 64, 128, 4, 2, 8>("r4_t64_u2"),
+    };
+    return v;
+}
+
+// ------------------------------------------------------------------------------
+//  context
+// ------------------------------------------------------------------------------
+struct nbx_ctx {
+    int n = 0, n_pad = 0, device = 0, rank = 0, world = 1, i_begin = 0, i_count = 0;
+    float dt = 0.1f, G = 6.67259e-11f, eps2 = 1e-3f;
+    int sm_count = 0, sm_clock_khz = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    float4 *pos[2] = {nullptr, nullptr};
+    int cur = 0;
+    float4 *vel = nullptr;
+    float4 *part = nullptr;
+    float4 *acc = nullptr;
+    int *tile_ticket = nullptr;
+    double *ke_part = nullptr;
+    int *counters = nullptr;   // [0]=ke_ticket [1]=dev_step [2]=dev_epoch
+    int *flags = nullptr;      // [kMaxWorld] peers publish their epoch here
+    double *ke_dev = nullptr;
+    int ke_cap = 0;
+    float *stage = nullptr;
+    size_t stage_floats = 0;
+    bool uploaded = false;
+
+    // configuration
+    int variant = 0, opt_splits = 0, opt_graph = -1, exchange = NBX_EXCHANGE_NCCL;
+    bool resolved = false;
+    int i_tiles = 0, j_splits = 1, ctas_per_sm = 0, use_graph = 0;
+
+    // graphs (2-step and 16-step replay units; both start and end on pos[0])
+    cudaGraphExec_t graph2 = nullptr, graph16 = nullptr;
+
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    bool p2p_ready = false;
+    float4 *peer_pos[2][nbx::kMaxWorld] = {};
+    int *peer_flags[nbx::kMaxWorld] = {};
+    std::vector<void *> ipc_opened;
+
+    long long kernel_launches = 0, aux_launches = 0;
+    double last_run_seconds = 0.0, kernel_seconds_total = 0.0;
+};
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static int resolve(nbx_ctx *c)
+{
+    if (c->resolved) return NBX_OK;
+    const Variant &v = variants()[c->variant];
+    CU(cudaSetDevice(c->device));
+    CU(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, v.threads, v.smem));
+    if (occ < 1) return fail(NBX_ERR_CUDA, "kernel variant %s cannot be resident", v.name);
+    c->ctas_per_sm = occ;
+    const int bi = v.threads * v.r2 * 2;
+    c->i_tiles = (c->i_count + bi - 1) / bi;
+
+    // j-split: equal CTAs quantise into waves of (SMs x resident CTAs); pick the split count
+    // whose last wave is fullest.  Keep >= 2 TMA tiles per split and prefer the smallest S
+    // within 1% of the best (fewer partials to park and combine).
+    int splits = c->opt_splits;
+    if (splits <= 0) {
+        const double wave = (double)c->sm_count * occ;
+        const int smax = std::max(1, std::min(64, c->n_pad / (2 * v.tj)));
+        double best = -1.0;
+        splits = 1;
+        for (int s = 1; s <= smax; ++s) {
+            const double ctas = (double)c->i_tiles * s;
+            const double eff = (ctas / wave) / std::ceil(ctas / wave);
+            if (eff > best + 0.01) { best = eff; splits = s; }
+        }
+    }
+    splits = std::max(1, std::min(splits, std::max(1, c->n_pad / 8)));
+    c->j_splits = splits;
+
+    if (c->opt_graph >= 0)
+        c->use_graph = c->opt_graph;
+    else   // launch latency matters below ~1 ms per step
+        c->use_graph = ((double)c->n_pad * (double)c->i_count < 2.5e9) ? 1 : 0;
+    if (c->world > 1 && c->exchange == NBX_EXCHANGE_NCCL) c->use_graph = 0;
+
+    if (c->part) { CU(cudaFree(c->part)); c->part = nullptr; }
+    if (c->tile_ticket) { CU(cudaFree(c->tile_ticket)); c->tile_ticket = nullptr; }
+    if (c->ke_part) { CU(cudaFree(c->ke_part)); c->ke_part = nullptr; }
+    if (splits > 1) CU(cudaMalloc(&c->part, (size_t)splits * c->i_count * sizeof(float4)));
+    CU(cudaMalloc(&c->tile_ticket, (size_t)c->i_tiles * sizeof(int)));
+    CU(cudaMemset(c->tile_ticket, 0, (size_t)c->i_tiles * sizeof(int)));
+    CU(cudaMalloc(&c->ke_part, (size_t)c->i_tiles * sizeof(double)));
+    if (c->graph2) { cudaGraphExecDestroy(c->graph2); c->graph2 = nullptr; }
+    if (c->graph16) { cudaGraphExecDestroy(c->graph16); c->graph16 = nullptr; }
+    c->resolved = true;
+    return NBX_OK;
+}
+
+static void fill_params(const nbx_ctx *c, StepParams &p, int in_buf, float4 *acc_out)
+{
+    std::memset(&p, 0, sizeof p);
+    p.pos_in = c->pos[in_buf];
+    p.pos_out = c->pos[in_buf ^ 1];
+    p.vel = c->vel;
+    p.part = c->part;
+    p.tile_ticket = c->tile_ticket;
+    p.ke_part = c->ke_part;
+    p.ke_ticket = c->counters + 0;
+    p.dev_step = c->counters + 1;
+    p.dev_epoch = c->counters + 2;
+    p.ke_out = c->ke_dev;
+    p.acc_out = acc_out;
+    p.n_pad = c->n_pad;
+    p.i_begin = c->i_begin;
+    p.i_count = c->i_count;
+    p.j_splits = c->j_splits;
+    p.dt = c->dt;
+    p.eps2 = c->eps2;
+    p.world = c->world;
+    p.rank = c->rank;
+    p.p2p = (acc_out == nullptr && c->world > 1 && c->exchange == NBX_EXCHANGE_P2P) ? 1 : 0;
+    if (p.p2p) {
+        for (int g = 0; g < c->world; ++g) {
+            p.peer_pos_out[g] = c->peer_pos[in_buf ^ 1][g];
+            p.peer_flags[g] = c->peer_flags[g];
+        }
+        p.my_flags = c->flags;
+    }
+}
+
+static int launch_step(nbx_ctx *c, int in_buf, float4 *acc_out = nullptr)
+{
+    const Variant &v = variants()[c->variant];
+    StepParams p;
+    fill_params(c, p, in_buf, acc_out);
+    void *args[] = {&p};
+    CU(cudaLaunchKernel(v.fn, dim3(c->i_tiles, c->j_splits), dim3(v.threads), args, v.smem, c->stream));
+    c->kernel_launches++;
+    return NBX_OK;
+}
+
+static int build_graph(nbx_ctx *c, int steps, cudaGraphExec_t *out)
+{
+    cudaGraph_t g = nullptr;
+    const long long before = c->kernel_launches;
+    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = NBX_OK;
+    for (int s = 0; s < steps && rc == NBX_OK; ++s) rc = launch_step(c, s & 1);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    c->kernel_launches = before;   // capturing is not launching
+    if (rc != NBX_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(NBX_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(NBX_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+    return NBX_OK;
+}
+
+static int ensure_ke(nbx_ctx *c, int nsteps)
+{
+    if (nsteps <= c->ke_cap) return NBX_OK;
+    // the graphs bake ke_dev's address in: drop them with the old buffer
+    if (c->graph2) { cudaGraphExecDestroy(c->graph2); c->graph2 = nullptr; }
+    if (c->graph16) { cudaGraphExecDestroy(c->graph16); c->graph16 = nullptr; }
+    if (c->ke_dev) CU(cudaFree(c->ke_dev));
+    c->ke_dev = nullptr;
+    const int cap = std::max(nsteps, 1024);
+    CU(cudaMalloc(&c->ke_dev, (size_t)cap * sizeof(double)));
+    c->ke_cap = cap;
+    return NBX_OK;
+}
+
+// Enqueue nsteps steps (and their exchanges) on c->stream; no host sync.
+static int enqueue_steps(nbx_ctx *c, int nsteps)
+{
+    const bool nccl_x = c->world > 1 && c->exchange == NBX_EXCHANGE_NCCL;
+    int left = nsteps;
+    if (c->use_graph && !nccl_x) {
+        if (c->cur == 1 && left > 0) {   // graphs start on pos[0]
+            int rc = launch_step(c, 1);
+            if (rc) return rc;
+            c->cur = 0;
+            --left;
+        }
+        if (left >= 16 && !c->graph16) { int rc = build_graph(c, 16, &c->graph16); if (rc) return rc; }
+        while (left >= 16) {
+            CU(cudaGraphLaunch(c->graph16, c->stream));
+            c->kernel_launches += 16;
+            left -= 16;
+        }
+        if (left >= 2 && !c->graph2) { int rc = build_graph(c, 2, &c->graph2); if (rc) return rc; }
+        while (left >= 2) {
+            CU(cudaGraphLaunch(c->graph2, c->stream));
+            c->kernel_launches += 2;
+            left -= 2;
+        }
+    }
+    while (left > 0) {
+        int rc = launch_step(c, c->cur);
+        if (rc) return rc;
+        c->cur ^= 1;
+        --left;
+        if (nccl_x) {
+            // in-place all-gather of the freshly written shard of pos[cur]
+            float4 *buf = c->pos[c->cur];
+            NC(g_nccl.AllGather(buf + c->i_begin, buf, (size_t)c->i_count * 4, ncclFloat, c->comm, c->stream));
+        }
+    }
+    return NBX_OK;
+}
+
+// ------------------------------------------------------------------------------
+//  C ABI
+// ------------------------------------------------------------------------------
+extern "C" {
+
+int nbx_abi_version(void) { return NBX_ABI_VERSION; }
+const char *nbx_last_error(void) { return g_err.c_str(); }
+
+int nbx_device_count(int *count)
+{
+    if (!count) return fail(NBX_ERR_ARG, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *count = n;
+    return NBX_OK;
+}
+
+int nbx_variant_count(void) { return (int)variants().size(); }
+const char *nbx_variant_name(int idx)
+{
+    if (idx < 0 || idx >= (int)variants().size()) return "";
+    return variants()[idx].name;
+}
+
+int nbx_create(nbx_ctx **out, int n, int device, int rank, int world, float dt, float G, float eps2)
+{
+    if (!out) return fail(NBX_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (n < 1) return fail(NBX_ERR_ARG, "n must be >= 1 (got %d)", n);
+    if (world < 1 || world > nbx::kMaxWorld || rank < 0 || rank >= world)
+        return fail(NBX_ERR_ARG, "bad rank/world %d/%d (world <= %d)", rank, world, nbx::kMaxWorld);
+    if (!(eps2 > 0.f)) return fail(NBX_ERR_ARG, "eps2 must be > 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(NBX_ERR_NODEVICE, "no CUDA device visible (libnbx has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(NBX_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(NBX_ERR_NODEVICE, "device %d is sm_%d%d; libnbx is built for sm_100a only", device, prop.major, prop.minor);
+
+    nbx_ctx *c = new nbx_ctx();
+    c->n = n; c->device = device; c->rank = rank; c->world = world;
+    c->dt = dt; c->G = G; c->eps2 = eps2;
+    c->n_pad = round_up(n, 8 * world);          // shards and TMA chunks stay 128-byte granular
+    c->i_count = c->n_pad / world;
+    c->i_begin = rank * c->i_count;
+    c->sm_count = prop.multiProcessorCount;
+    c->sm_clock_khz = prop.clockRate;
+    auto bail = [&](int rc) { nbx_destroy(c); return rc; };
+#define CUB(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return bail(fail(NBX_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_))); \
+    } while (0)
+    CUB(cudaSetDevice(device));
+    CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreate(&c->ev0));
+    CUB(cudaEventCreate(&c->ev1));
+    CUB(cudaMalloc(&c->pos[0], (size_t)c->n_pad * sizeof(float4)));
+    CUB(cudaMalloc(&c->pos[1], (size_t)c->n_pad * sizeof(float4)));
+    CUB(cudaMalloc(&c->vel, (size_t)c->i_count * sizeof(float4)));
+    CUB(cudaMalloc(&c->counters, 4 * sizeof(int)));
+    CUB(cudaMemset(c->counters, 0, 4 * sizeof(int)));
+    CUB(cudaMalloc(&c->flags, nbx::kMaxWorld * sizeof(int)));
+    CUB(cudaMemset(c->flags, 0, nbx::kMaxWorld * sizeof(int)));
+#undef CUB
+    *out = c;
+    return NBX_OK;
+}
+
+void nbx_destroy(nbx_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->graph2) cudaGraphExecDestroy(c->graph2);
+    if (c->graph16) cudaGraphExecDestroy(c->graph16);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    cudaFree(c->pos[0]); cudaFree(c->pos[1]); cudaFree(c->vel); cudaFree(c->part); cudaFree(c->acc);
+    cudaFree(c->tile_ticket); cudaFree(c->ke_part); cudaFree(c->counters); cudaFree(c->flags);
+    cudaFree(c->ke_dev); cudaFree(c->stage);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+}
+
+int nbx_set_option(nbx_ctx *c, const char *key, long long value)
+{
+    if (!c || !key) return fail(NBX_ERR_ARG, "NULL argument");
+    const std::string k(key);
+    if (k == "j_splits") {
+        if (value < 0 || value > 4096) return fail(NBX_ERR_ARG, "j_splits out of range");
+        c->opt_splits = (int)value;
+    } else if (k == "graph") {
+        c->opt_graph = value < 0 ? -1 : (value ? 1 : 0);
+    } else if (k == "exchange") {
+        if (value != NBX_EXCHANGE_NCCL && value != NBX_EXCHANGE_P2P) return fail(NBX_ERR_ARG, "unknown exchange %lld", value);
+        c->exchange = (int)value;
+    } else if (k == "variant") {
+        if (value < 0 || value >= (long long)variants().size()) return fail(NBX_ERR_ARG, "variant out of range");
+        c->variant = (int)value;
+    } else {
+        return fail(NBX_ERR_ARG, "unknown option '%s'", key);
+    }
+    c->resolved = false;
+    return NBX_OK;
+}
+
+int nbx_get_info(const nbx_ctx *c, nbx_info *o)
+{
+    if (!c || !o) return fail(NBX_ERR_ARG, "NULL argument");
+    const Variant &v = variants()[c->variant];
+    std::memset(o, 0, sizeof *o);
+    o->abi_version = NBX_ABI_VERSION;
+    o->device = c->device; o->sm_count = c->sm_count; o->sm_clock_khz = c->sm_clock_khz;
+    o->n = c->n; o->n_pad = c->n_pad; o->rank = c->rank; o->world = c->world;
+    o->i_begin = c->i_begin; o->i_count = c->i_count;
+    o->threads = v.threads; o->bodies_per_thread = 2 * v.r2; o->tile_bodies = v.tj; o->stages = v.stages;
+    o->i_tiles = c->i_tiles; o->j_splits = c->j_splits; o->ctas_per_sm = c->ctas_per_sm;
+    o->use_graph = c->use_graph; o->exchange = c->exchange;
+    o->kernel_launches = c->kernel_launches; o->aux_launches = c->aux_launches;
+    o->last_run_seconds = c->last_run_seconds; o->kernel_seconds_total = c->kernel_seconds_total;
+    return NBX_OK;
+}
+
+static int ensure_stage(nbx_ctx *c, size_t floats)
+{
+    if (floats <= c->stage_floats) return NBX_OK;
+    if (c->stage) CU(cudaFree(c->stage));
+    c->stage = nullptr;
+    CU(cudaMalloc(&c->stage, floats * sizeof(float)));
+    c->stage_floats = floats;
+    return NBX_OK;
+}
+
+int nbx_upload(nbx_ctx *c, const float *px, const float *py, const float *pz,
+               const float *vx, const float *vy, const float *vz, const float *mass)
+{
+    if (!c || !px || !py || !pz || !vx || !vy || !vz || !mass) return fail(NBX_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->n;
+    int rc = ensure_stage(c, 7 * n);
+    if (rc) return rc;
+    const float *src[7] = {px, py, pz, vx, vy, vz, mass};
+    for (int k = 0; k < 7; ++k)
+        CU(cudaMemcpyAsync(c->stage + k * n, src[k], n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    const int recs = c->n_pad / 2;
+    nbx::pack_kernel<<<(recs + 255) / 256, 256, 0, c->stream>>>(c->stage, c->n, c->n_pad, c->i_begin, c->i_count,
+                                                                c->G, c->pos[0], c->pos[1], c->vel);
+    CU(cudaGetLastError());
+    c->aux_launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    c->cur = 0;
+    c->uploaded = true;
+    return NBX_OK;
+}
+
+int nbx_download(nbx_ctx *c, float *px, float *py, float *pz, float *vx, float *vy, float *vz)
+{
+    if (!c) return fail(NBX_ERR_ARG, "NULL context");
+    if (!c->uploaded) return fail(NBX_ERR_STATE, "download before upload");
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->n;
+    int rc = ensure_stage(c, 7 * n);
+    if (rc) return rc;
+    nbx::unpack_kernel<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->pos[c->cur], c->vel, c->n, c->i_begin,
+                                                                  c->i_count, c->stage);
+    CU(cudaGetLastError());
+    c->aux_launches++;
+    float *dst[3] = {px, py, pz};
+    for (int k = 0; k < 3; ++k)
+        if (dst[k]) CU(cudaMemcpyAsync(dst[k], c->stage + k * n, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    const size_t lo = (size_t)std::min(c->i_begin, c->n);
+    const size_t hi = (size_t)std::min(c->i_begin + c->i_count, c->n);
+    float *vdst[3] = {vx, vy, vz};
+    for (int k = 0; k < 3; ++k)
+        if (vdst[k] && hi > lo)
+            CU(cudaMemcpyAsync(vdst[k] + lo, c->stage + (3 + k) * n + lo, (hi - lo) * sizeof(float),
+                               cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return NBX_OK;
+}
+
+static int check_runnable(nbx_ctx *c, int nsteps)
+{
+    if (!c) return fail(NBX_ERR_ARG, "NULL context");
+    if (nsteps < 0) return fail(NBX_ERR_ARG, "nsteps must be >= 0");
+    if (!c->uploaded) return fail(NBX_ERR_STATE, "run before upload");
+    if (c->world > 1) {
+        if (!c->comm) return fail(NBX_ERR_STATE, "world > 1 needs nbx_comm_init / nbx_comm_init_all first");
+        if (c->exchange == NBX_EXCHANGE_P2P && !c->p2p_ready)
+            return fail(NBX_ERR_STATE, "P2P exchange needs nbx_p2p_attach first");
+    }
+    return NBX_OK;
+}
+
+int nbx_run(nbx_ctx *c, int nsteps, double *kenergy_out, double *seconds_out)
+{
+    int rc = check_runnable(c, nsteps);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    if ((rc = resolve(c))) return rc;
+    if ((rc = ensure_ke(c, nsteps))) return rc;
+    CU(cudaMemsetAsync(c->counters + 1, 0, sizeof(int), c->stream));   // dev_step = 0
+    CU(cudaEventRecord(c->ev0, c->stream));
+    if ((rc = enqueue_steps(c, nsteps))) return rc;
+    if (c->world > 1 && nsteps > 0)
+        NC(g_nccl.AllReduce(c->ke_dev, c->ke_dev, (size_t)nsteps, ncclDouble, ncclSum, c->comm, c->stream));
+    CU(cudaEventRecord(c->ev1, c->stream));
+    if (kenergy_out && nsteps > 0)
+        CU(cudaMemcpyAsync(kenergy_out, c->ke_dev, (size_t)nsteps * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_run_seconds = ms * 1e-3;
+    c->kernel_seconds_total += c->last_run_seconds;
+    if (seconds_out) *seconds_out = c->last_run_seconds;
+    return NBX_OK;
+}
+
+int nbx_run_group(nbx_ctx **ctxs, int count, int nsteps, double *kenergy_out, double *seconds_out)
+{
+    if (!ctxs || count < 1) return fail(NBX_ERR_ARG, "bad context array");
+    int rc;
+    for (int g = 0; g < count; ++g) {
+        if ((rc = check_runnable(ctxs[g], nsteps))) return rc;
+        if (ctxs[g]->world != count || ctxs[g]->rank != g) return fail(NBX_ERR_ARG, "ctxs[%d] is not rank %d of %d", g, g, count);
+        CU(cudaSetDevice(ctxs[g]->device));
+        if ((rc = resolve(ctxs[g]))) return rc;
+        if ((rc = ensure_ke(ctxs[g], nsteps))) return rc;
+        CU(cudaMemsetAsync(ctxs[g]->counters + 1, 0, sizeof(int), ctxs[g]->stream));
+        CU(cudaEventRecord(ctxs[g]->ev0, ctxs[g]->stream));
+    }
+    const bool nccl_x = count > 1 && ctxs[0]->exchange == NBX_EXCHANGE_NCCL;
+    if (!nccl_x) {
+        for (int g = 0; g < count; ++g) {
+            CU(cudaSetDevice(ctxs[g]->device));
+            if ((rc = enqueue_steps(ctxs[g], nsteps))) return rc;
+        }
+    } else {
+        for (int s = 0; s < nsteps; ++s) {
+            for (int g = 0; g < count; ++g) {
+                nbx_ctx *c = ctxs[g];
+                CU(cudaSetDevice(c->device));
+                if ((rc = launch_step(c, c->cur))) return rc;
+                c->cur ^= 1;
+            }
+            NC(g_nccl.GroupStart());
+            for (int g = 0; g < count; ++g) {
+                nbx_ctx *c = ctxs[g];
+                float4 *buf = c->pos[c->cur];
+                NC(g_nccl.AllGather(buf + c->i_begin, buf, (size_t)c->i_count * 4, ncclFloat, c->comm, c->stream));
+            }
+            NC(g_nccl.GroupEnd());
+        }
+    }
+    std::vector<double> tmp((size_t)std::max(nsteps, 1));
+    if (kenergy_out) std::fill(kenergy_out, kenergy_out + nsteps, 0.0);
+    double tmax = 0.0;
+    for (int g = 0; g < count; ++g) {
+        nbx_ctx *c = ctxs[g];
+        CU(cudaSetDevice(c->device));
+        CU(cudaEventRecord(c->ev1, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->last_run_seconds = ms * 1e-3;
+        c->kernel_seconds_total += c->last_run_seconds;
+        tmax = std::max(tmax, c->last_run_seconds);
+        if (kenergy_out && nsteps > 0) {
+            CU(cudaMemcpy(tmp.data(), c->ke_dev, (size_t)nsteps * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int s = 0; s < nsteps; ++s) kenergy_out[s] += tmp[s];   // rank order: deterministic
+        }
+    }
+    if (seconds_out) *seconds_out = tmax;
+    return NBX_OK;
+}
+
+int nbx_accelerations(nbx_ctx *c, float *ax, float *ay, float *az)
+{
+    if (!c || !ax || !ay || !az) return fail(NBX_ERR_ARG, "NULL argument");
+    if (!c->uploaded) return fail(NBX_ERR_STATE, "accelerations before upload");
+    CU(cudaSetDevice(c->device));
+    int rc = resolve(c);
+    if (rc) return rc;
+    if (!c->acc) CU(cudaMalloc(&c->acc, (size_t)c->i_count * sizeof(float4)));
+    if ((rc = launch_step(c, c->cur, c->acc))) return rc;
+    std::vector<float4> h((size_t)c->i_count);
+    CU(cudaMemcpyAsync(h.data(), c->acc, h.size() * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < c->i_count; ++i) { ax[i] = h[i].x; ay[i] = h[i].y; az[i] = h[i].z; }
+    return NBX_OK;
+}
+
+int nbx_simulate(int n, int nsteps, float dt, float G, float eps2,
+                 float *px, float *py, float *pz, float *vx, float *vy, float *vz,
+                 const float *mass, double *kenergy_out, double *seconds_out)
+{
+    nbx_ctx *c = nullptr;
+    int rc = nbx_create(&c, n, 0, 0, 1, dt, G, eps2);
+    if (rc) return rc;
+    if ((rc = nbx_upload(c, px, py, pz, vx, vy, vz, mass)) == NBX_OK)
+        if ((rc = nbx_run(c, nsteps, kenergy_out, seconds_out)) == NBX_OK)
+            rc = nbx_download(c, px, py, pz, vx, vy, vz);
+    nbx_destroy(c);
+    return rc;
+}
+
+// ---- multi-GPU plumbing --------------------------------------------------------
+int nbx_comm_unique_id(void *id_out)
+{
+    if (!id_out) return fail(NBX_ERR_ARG, "id_out is NULL");
+    int rc = nccl_load();
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == NBX_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    std::memcpy(id_out, &id, sizeof id);
+    return NBX_OK;
+}
+
+int nbx_comm_init(nbx_ctx *c, const void *id_bytes)
+{
+    if (!c || !id_bytes) return fail(NBX_ERR_ARG, "NULL argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id_bytes, sizeof id);
+    NC(g_nccl.CommInitRank(&c->comm, c->world, id, c->rank));
+    return NBX_OK;
+}
+
+int nbx_comm_init_all(nbx_ctx **ctxs, int count)
+{
+    if (!ctxs || count < 1 || count > nbx::kMaxWorld) return fail(NBX_ERR_ARG, "bad context array");
+    int rc = nccl_load();
+    if (rc) return rc;
+    std::vector<int> devs(count);
+    std::vector<ncclComm_t> comms(count);
+    for (int g = 0; g < count; ++g) {
+        if (!ctxs[g] || ctxs[g]->world != count || ctxs[g]->rank != g) return fail(NBX_ERR_ARG, "ctxs[%d] is not rank %d of %d", g, g, count);
+        devs[g] = ctxs[g]->device;
+    }
+    NC(g_nccl.CommInitAll(comms.data(), count, devs.data()));
+    for (int g = 0; g < count; ++g) ctxs[g]->comm = comms[g];
+    return NBX_OK;
+}
+
+struct P2PBlob {
+    uint32_t magic;
+    int32_t rank;
+    int64_t pid;
+    void *raw[3];                    // pos[0], pos[1], flags (valid inside the exporting process)
+    int32_t device;
+    int32_t pad;
+    cudaIpcMemHandle_t h[3];
+};
+static_assert(sizeof(P2PBlob) <= NBX_P2P_BLOB_BYTES, "P2P blob size");
+
+int nbx_p2p_export(nbx_ctx *c, void *blob_out)
+{
+    if (!c || !blob_out) return fail(NBX_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    P2PBlob b;
+    std::memset(&b, 0, sizeof b);
+    b.magic = 0x4e425850u;
+    b.rank = c->rank;
+    b.pid = (int64_t)getpid();
+    b.device = c->device;
+    b.raw[0] = c->pos[0]; b.raw[1] = c->pos[1]; b.raw[2] = c->flags;
+    CU(cudaIpcGetMemHandle(&b.h[0], c->pos[0]));
+    CU(cudaIpcGetMemHandle(&b.h[1], c->pos[1]));
+    CU(cudaIpcGetMemHandle(&b.h[2], c->flags));
+    std::memset(blob_out, 0, NBX_P2P_BLOB_BYTES);
+    std::memcpy(blob_out, &b, sizeof b);
+    return NBX_OK;
+}
+
+int nbx_p2p_attach(nbx_ctx *c, const void *blobs)
+{
+    if (!c || !blobs) return fail(NBX_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const unsigned char *base = static_cast<const unsigned char *>(blobs);
+    for (int g = 0; g < c->world; ++g) {
+        P2PBlob b;
+        std::memcpy(&b, base + (size_t)g * NBX_P2P_BLOB_BYTES, sizeof b);
+        if (b.magic != 0x4e425850u || b.rank != g) return fail(NBX_ERR_ARG, "blob %d is malformed", g);
+        if (g == c->rank) {
+            c->peer_pos[0][g] = c->pos[0]; c->peer_pos[1][g] = c->pos[1]; c->peer_flags[g] = c->flags;
+            continue;
+        }
+        void *ptr[3];
+        if (b.pid == (int64_t)getpid()) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, c->device, b.device));
+            if (!can) return fail(NBX_ERR_CUDA, "device %d cannot access peer %d", c->device, b.device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(NBX_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", b.device, cudaGetErrorString(e));
+            cudaGetLastError();
+            for (int k = 0; k < 3; ++k) ptr[k] = b.raw[k];
+        } else {
+            for (int k = 0; k < 3; ++k) {
+                CU(cudaIpcOpenMemHandle(&ptr[k], b.h[k], cudaIpcMemLazyEnablePeerAccess));
+                c->ipc_opened.push_back(ptr[k]);
+            }
+        }
+        c->peer_pos[0][g] = static_cast<float4 *>(ptr[0]);
+        c->peer_pos[1][g] = static_cast<float4 *>(ptr[1]);
+        c->peer_flags[g] = static_cast<int *>(ptr[2]);
+    }
+    c->p2p_ready = true;
+    return NBX_OK;
+}
+
+// ---- host helpers ----------------------------------------------------------------
+void nbx_ic_uniform(int n, float *px, float *py, float *pz, float *vx, float *vy, float *vz, float *mass)
+{
+    nbx_ic::uniform_pos(n, px, py, pz);
+    nbx_ic::uniform_vel(n, vx, vy, vz);
+    nbx_ic::uniform_mass(n, mass);
+}
+
+void nbx_ic_plummer(int n, float *px, float *py, float *pz, float *vx, float *vy, float *vz, float *mass)
+{
+    nbx_ic::plummer_pos(n, px, py, pz);
+    nbx_ic::uniform_vel(n, vx, vy, vz);
+    nbx_ic::uniform_mass(n, mass);
+}
+
+double nbx_gflop_per_step(int n)
+{
+    const double nd = (double)n;
+    return 1e-9 * ((11. + 18.) * nd * nd + nd * 19.);
+}
+
+int nbx_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(NBX_ERR_ARG, "ptr is NULL");
+    CU(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return NBX_OK;
+}
+
+int nbx_host_free(void *ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
+    return NBX_OK;
+}
+
+}  // extern "C"

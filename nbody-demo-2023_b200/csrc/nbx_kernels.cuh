@@ -1,0 +1,426 @@
+// nbx_kernels.cuh -- sm_100a kernels for the O(N^2) force + Euler + kinetic-energy step.
+//
+// What the reference does per step (ver2/GSimulation.cpp:130-173, float):
+//   a_i  = sum_j G m_j (r_j - r_i) (|r_j - r_i|^2 + eps2)^(-3/2)     (all j, self term = 0)
+//   v_i += a_i dt ; r_i += v_i dt ; kenergy = 0.5 sum_i m_i |v_i|^2
+// and its only CUDA kernel (ver5_all/programming_models/cuda/Compute.cu:31-66) is one
+// thread per i streaming j from global memory, with the update done on the host.
+//
+// This file is a different design, for B200:
+//   * bodies live in HBM "pair-packed": one 32-byte record per two bodies,
+//     {x0,x1,y0,y1 | z0,z1,Gm0,Gm1}.  A record is at once the TMA unit, the operand
+//     layout of Blackwell's packed FP32 instructions (FFMA2/FADD2/FMUL2: two lanes of
+//     a 64-bit register pair) and the multi-GPU exchange unit;
+//   * each CTA streams j-records through a ring of shared-memory stages filled by
+//     1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), 4 stages deep;
+//   * each thread register-blocks R = 2*R2 i-bodies and evaluates every (i, j-pair)
+//     with 12 packed FP32 instructions + 2 MUFU.RSQ, i.e. 12 FP32-pipe lane-ops and
+//     7 issue slots per pair instead of 13 -- the FP32 pipe, not issue, is the limit;
+//   * the Euler update, the kinetic-energy reduction (deterministic: per-CTA partial,
+//     last CTA sums in tile order) and, on several GPUs, the NVLink stores of the
+//     updated records into every peer's replica all run in the same kernel's epilogue;
+//   * a j-split grid (gridDim.y) with a last-arriver combine in fixed split order
+//     fills the 148 SMs when N/BI CTAs would not.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nbx {
+
+constexpr int kMaxWorld = 8;
+
+struct StepParams {
+    const float4 *pos_in;   // pair-packed records, n_pad bodies = n_pad float4s
+    float4 *pos_out;        // same layout, the other half of the ping-pong
+    float4 *vel;            // shard-local: (vx, vy, vz, m) per body
+    float4 *part;           // [j_splits][i_count] partial accelerations
+    int *tile_ticket;       // [i_tiles] arrival counters (self-resetting)
+    double *ke_part;        // [i_tiles]
+    int *ke_ticket;         // [1]
+    double *ke_out;         // [steps] kinetic energy, slot = *dev_step
+    int *dev_step;          // step index inside the current run (reset by the host per run)
+    int *dev_epoch;         // steps completed since create (never reset; P2P flag value)
+    float4 *acc_out;        // non-null: store accelerations, do not update (nbx_accelerations)
+    int n_pad;
+    int i_begin, i_count;
+    int j_splits;
+    float dt, eps2;
+    // P2P exchange (world > 1 and exchange == P2P): peers' replicas and completion flags
+    int world, rank, p2p;
+    float4 *peer_pos_out[kMaxWorld];  // [g] = rank g's pos_out (self entry unused)
+    int *peer_flags[kMaxWorld];       // [g] = rank g's flags[kMaxWorld]; we write slot [rank]
+    const int *my_flags;              // this rank's flags[kMaxWorld]
+};
+
+// ------------------------------------------------------------------------------
+//  PTX helpers: mbarrier + 1-D TMA bulk copy (SASS: SYNCS.*, UBLKCP)
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // one MUFU.RSQ; x >= eps2 > 0 always
+    return y;
+}
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Shared-memory footprint of one CTA (host uses the same formula).
+template <int THREADS, int TJ, int STAGES>
+constexpr int step_smem_bytes()
+{
+    return STAGES * TJ * 16 + 2 * STAGES * 8 + (THREADS / 32) * 8 + 16;
+}
+
+// ------------------------------------------------------------------------------
+//  The step kernel.
+//    R2      i-body PAIRS register-blocked per thread (R = 2*R2 bodies)
+//    THREADS CTA size;  BI = THREADS*R i-bodies per CTA
+//    TJ      j-bodies per TMA stage (multiple of 8)
+//    STAGES  ring depth (>= 3: one being read, one landed, one in flight)
+//    UNROLL  j-records per inner-loop trip (1, 2 or 4)
+//    MINB    __launch_bounds__ min CTAs per SM
+//  grid = (i_tiles, j_splits)
+// ------------------------------------------------------------------------------
+template <int R2, int THREADS, int TJ, int STAGES, int UNROLL, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_constant__ StepParams p)
+{
+    constexpr int R = 2 * R2;
+    constexpr int WARPS = THREADS / 32;
+    static_assert(TJ % 8 == 0 && STAGES >= 3 && (UNROLL == 1 || UNROLL == 2 || UNROLL == 4), "shape");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + STAGES * TJ * 16);
+    uint64_t *empty = full + STAGES;
+    double *red = reinterpret_cast<double *>(empty + STAGES);
+    int *s_flag = reinterpret_cast<int *>(red + WARPS);
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int split = blockIdx.y;
+
+    // ---- j range of this CTA, in 8-body chunks so every TMA copy is 128-byte granular
+    const int chunks = p.n_pad >> 3;
+    const int jb = (int)(((long long)chunks * split) / p.j_splits) << 3;
+    const int je = (int)(((long long)chunks * (split + 1)) / p.j_splits) << 3;
+    const int ntiles = (je - jb + TJ - 1) / TJ;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], WARPS);
+        }
+        mbar_fence_init();
+        // P2P exchange: every rank must have finished the previous step (its epilogue wrote
+        // into OUR pos_in) before we read it.  Peers run on other GPUs; no kernel on this
+        // GPU is waited on.
+        if (p.p2p) {
+            const int epoch = *p.dev_epoch;
+            for (int g = 0; g < p.world; ++g)
+                if (g != p.rank)
+                    while (ld_acquire_sys(&p.my_flags[g]) < epoch) { }
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+    }
+    __syncthreads();
+
+    auto issue_tile = [&](int t) {
+        const int j0 = jb + t * TJ;
+        const int cnt = min(TJ, je - j0);
+        const int st = t % STAGES;
+        mbar_expect_tx(&full[st], (uint32_t)cnt * 16u);
+        tma_load_1d(tiles + st * TJ, p.pos_in + j0, (uint32_t)cnt * 16u, &full[st]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int t = 0; t < STAGES - 2; ++t)
+            if (t < ntiles) issue_tile(t);
+    }
+
+    // ---- my i-bodies: R2 records, negated and duplicated for the packed subtract
+    float2 nx[R], ny[R], nz[R];
+    float2 ax[R], ay[R], az[R];
+    const int pair_base = tile * (THREADS * R2) + tid;   // shard-local record index of k = 0
+#pragma unroll
+    for (int k = 0; k < R2; ++k) {
+        int ip = pair_base + k * THREADS;
+        ip = min(ip, (p.i_count >> 1) - 1);               // clamp: tail threads redo the last record
+        const size_t gp = (size_t)(p.i_begin >> 1) + ip;
+        const float4 q0 = __ldg(&p.pos_in[2 * gp]);
+        const float4 q1 = __ldg(&p.pos_in[2 * gp + 1]);
+        nx[2 * k] = make_float2(-q0.x, -q0.x); nx[2 * k + 1] = make_float2(-q0.y, -q0.y);
+        ny[2 * k] = make_float2(-q0.z, -q0.z); ny[2 * k + 1] = make_float2(-q0.w, -q0.w);
+        nz[2 * k] = make_float2(-q1.x, -q1.x); nz[2 * k + 1] = make_float2(-q1.y, -q1.y);
+    }
+#pragma unroll
+    for (int b = 0; b < R; ++b) ax[b] = ay[b] = az[b] = make_float2(0.f, 0.f);
+    const float2 eps2v = make_float2(p.eps2, p.eps2);
+
+    // ---- sweep the j tiles
+    for (int t = 0; t < ntiles; ++t) {
+        if (tid == 0) {
+            const int u = t + STAGES - 2;                  // refill two tiles behind the reader
+            if (u < ntiles) {
+                if (u >= STAGES) mbar_wait(&empty[u % STAGES], ((u / STAGES) - 1) & 1);
+                issue_tile(u);
+            }
+        }
+        const int st = t % STAGES;
+        mbar_wait(&full[st], (t / STAGES) & 1);
+        const float4 *rec = tiles + st * TJ;
+        const int nrec = min(TJ, je - (jb + t * TJ)) >> 1;  // records in this tile (multiple of 4)
+#pragma unroll 1
+        for (int jr = 0; jr < nrec; jr += UNROLL) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const float4 q0 = rec[2 * (jr + u)];
+                const float4 q1 = rec[2 * (jr + u) + 1];
+                const float2 xj = make_float2(q0.x, q0.y), yj = make_float2(q0.z, q0.w);
+                const float2 zj = make_float2(q1.x, q1.y), mj = make_float2(q1.z, q1.w);
+#pragma unroll
+                for (int b = 0; b < R; ++b) {
+                    const float2 dx = __fadd2_rn(xj, nx[b]);
+                    const float2 dy = __fadd2_rn(yj, ny[b]);
+                    const float2 dz = __fadd2_rn(zj, nz[b]);
+                    float2 r2 = __ffma2_rn(dx, dx, eps2v);
+                    r2 = __ffma2_rn(dy, dy, r2);
+                    r2 = __ffma2_rn(dz, dz, r2);
+                    const float2 inv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+                    const float2 inv2 = __fmul2_rn(inv, inv);
+                    const float2 mi = __fmul2_rn(mj, inv);
+                    const float2 s = __fmul2_rn(inv2, mi);
+                    ax[b] = __ffma2_rn(dx, s, ax[b]);
+                    ay[b] = __ffma2_rn(dy, s, ay[b]);
+                    az[b] = __ffma2_rn(dz, s, az[b]);
+                }
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+    }
+
+    // ---- fold the two j lanes
+    float fx[R], fy[R], fz[R];
+#pragma unroll
+    for (int b = 0; b < R; ++b) {
+        fx[b] = ax[b].x + ax[b].y;
+        fy[b] = ay[b].x + ay[b].y;
+        fz[b] = az[b].x + az[b].y;
+    }
+
+    // ---- j-split: park partials, the last CTA of this i-tile adds them in split order
+    if (p.j_splits > 1) {
+        float4 *mine = p.part + (size_t)split * p.i_count;
+#pragma unroll
+        for (int k = 0; k < R2; ++k) {
+            const int ip = pair_base + k * THREADS;
+            if (2 * ip < p.i_count) {
+                mine[2 * ip] = make_float4(fx[2 * k], fy[2 * k], fz[2 * k], 0.f);
+                mine[2 * ip + 1] = make_float4(fx[2 * k + 1], fy[2 * k + 1], fz[2 * k + 1], 0.f);
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *s_flag = (atomicAdd(&p.tile_ticket[tile], 1) == p.j_splits - 1);
+        __syncthreads();
+        if (!*s_flag) return;
+        __threadfence();
+        if (tid == 0) p.tile_ticket[tile] = 0;
+#pragma unroll
+        for (int k = 0; k < R2; ++k) {
+            const int ip = pair_base + k * THREADS;
+            if (2 * ip < p.i_count) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float sx = 0.f, sy = 0.f, sz = 0.f;
+                    for (int s = 0; s < p.j_splits; ++s) {
+                        const float4 v = __ldcg(&p.part[(size_t)s * p.i_count + 2 * ip + h]);
+                        sx += v.x; sy += v.y; sz += v.z;
+                    }
+                    fx[2 * k + h] = sx; fy[2 * k + h] = sy; fz[2 * k + h] = sz;
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: Euler update (ver2:153-165), energy term (ver2:167-170), exchange
+    double e = 0.0;
+#pragma unroll
+    for (int k = 0; k < R2; ++k) {
+        const int ip = pair_base + k * THREADS;
+        if (2 * ip >= p.i_count) continue;
+        if (p.acc_out != nullptr) {
+            p.acc_out[2 * ip] = make_float4(fx[2 * k], fy[2 * k], fz[2 * k], 0.f);
+            p.acc_out[2 * ip + 1] = make_float4(fx[2 * k + 1], fy[2 * k + 1], fz[2 * k + 1], 0.f);
+            continue;
+        }
+        float4 v0 = p.vel[2 * ip], v1 = p.vel[2 * ip + 1];
+        v0.x = fmaf(fx[2 * k], p.dt, v0.x); v0.y = fmaf(fy[2 * k], p.dt, v0.y); v0.z = fmaf(fz[2 * k], p.dt, v0.z);
+        v1.x = fmaf(fx[2 * k + 1], p.dt, v1.x); v1.y = fmaf(fy[2 * k + 1], p.dt, v1.y); v1.z = fmaf(fz[2 * k + 1], p.dt, v1.z);
+        p.vel[2 * ip] = v0;
+        p.vel[2 * ip + 1] = v1;
+        const float4 r0 = make_float4(fmaf(v0.x, p.dt, -nx[2 * k].x), fmaf(v1.x, p.dt, -nx[2 * k + 1].x),
+                                      fmaf(v0.y, p.dt, -ny[2 * k].x), fmaf(v1.y, p.dt, -ny[2 * k + 1].x));
+        const float2 r1 = make_float2(fmaf(v0.z, p.dt, -nz[2 * k].x), fmaf(v1.z, p.dt, -nz[2 * k + 1].x));
+        const size_t gp = (size_t)(p.i_begin >> 1) + ip;
+        p.pos_out[2 * gp] = r0;
+        *reinterpret_cast<float2 *>(&p.pos_out[2 * gp + 1]) = r1;      // Gm0,Gm1 never change
+        if (p.p2p) {
+            for (int g = 0; g < p.world; ++g) {
+                if (g == p.rank) continue;
+                float4 *dst = p.peer_pos_out[g];
+                dst[2 * gp] = r0;                                       // NVLink store
+                *reinterpret_cast<float2 *>(&dst[2 * gp + 1]) = r1;
+            }
+        }
+        e += (double)(v0.w * (v0.x * v0.x + v0.y * v0.y + v0.z * v0.z));
+        e += (double)(v1.w * (v1.x * v1.x + v1.y * v1.y + v1.z * v1.z));
+    }
+    if (p.acc_out != nullptr) return;
+
+    // ---- kinetic energy: warp shuffle -> smem -> per-tile partial -> last CTA sums in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if ((tid & 31) == 0) red[tid >> 5] = e;
+    if (p.p2p) __threadfence_system();   // my peer stores are visible before my ticket is
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < WARPS; ++w) s += red[w];
+        p.ke_part[tile] = s;
+        __threadfence();
+        *s_flag = (atomicAdd(p.ke_ticket, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*s_flag) return;
+    __threadfence();
+    double s = 0.0;
+    for (int i = tid; i < (int)gridDim.x; i += THREADS) s += __ldcg(&p.ke_part[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < WARPS; ++w) tot += red[w];
+        const int step = *p.dev_step;
+        p.ke_out[step] = 0.5 * tot;
+        *p.dev_step = step + 1;
+        *p.ke_ticket = 0;
+        const int epoch = *p.dev_epoch + 1;
+        *p.dev_epoch = epoch;
+        if (p.p2p) {
+            __threadfence_system();
+            for (int g = 0; g < p.world; ++g)
+                if (g != p.rank) st_release_sys(&p.peer_flags[g][p.rank], epoch);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------
+//  Layout kernels: host SoA staging <-> pair-packed records.
+// ------------------------------------------------------------------------------
+// stage = 7 arrays of n floats: px py pz vx vy vz mass.  Bodies >= n are zero-mass padding.
+__global__ void pack_kernel(const float *__restrict__ stage, int n, int n_pad, int i_begin, int i_count,
+                            float G, float4 *__restrict__ pos_a, float4 *__restrict__ pos_b,
+                            float4 *__restrict__ vel)
+{
+    const int rec = blockIdx.x * blockDim.x + threadIdx.x;   // record = body pair
+    if (2 * rec >= n_pad) return;
+    float x[2], y[2], z[2], m[2], vx[2], vy[2], vz[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = 2 * rec + h;
+        const bool live = i < n;
+        x[h] = live ? stage[i] : 0.f;
+        y[h] = live ? stage[(size_t)n + i] : 0.f;
+        z[h] = live ? stage[2 * (size_t)n + i] : 0.f;
+        vx[h] = live ? stage[3 * (size_t)n + i] : 0.f;
+        vy[h] = live ? stage[4 * (size_t)n + i] : 0.f;
+        vz[h] = live ? stage[5 * (size_t)n + i] : 0.f;
+        m[h] = live ? stage[6 * (size_t)n + i] : 0.f;
+    }
+    const float4 q0 = make_float4(x[0], x[1], y[0], y[1]);
+    const float4 q1 = make_float4(z[0], z[1], G * m[0], G * m[1]);
+    pos_a[2 * rec] = q0; pos_a[2 * rec + 1] = q1;
+    pos_b[2 * rec] = q0; pos_b[2 * rec + 1] = q1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int li = 2 * rec + h - i_begin;
+        if (li >= 0 && li < i_count) vel[li] = make_float4(vx[h], vy[h], vz[h], m[h]);
+    }
+}
+
+// stage = 6 arrays of n floats: px py pz (all bodies) vx vy vz (this shard's range only).
+__global__ void unpack_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ vel, int n,
+                              int i_begin, int i_count, float *__restrict__ stage)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *rec = reinterpret_cast<const float *>(pos + 2 * (size_t)(i >> 1));
+    const int h = i & 1;
+    stage[i] = rec[h];
+    stage[(size_t)n + i] = rec[2 + h];
+    stage[2 * (size_t)n + i] = rec[4 + h];
+    const int li = i - i_begin;
+    if (li >= 0 && li < i_count) {
+        const float4 v = vel[li];
+        stage[3 * (size_t)n + i] = v.x;
+        stage[4 * (size_t)n + i] = v.y;
+        stage[5 * (size_t)n + i] = v.z;
+    }
+}
+
+}  // namespace nbx

@@ -1,0 +1,273 @@
+"""GPU suite: the CUDA path (through the C ABI / the CLI) against the oracle, the
+committed reference fixtures and size-independent properties.
+
+Tolerances (BASELINE.json north_star): per-step kinetic energy within 1e-4 relative,
+positions within 1e-4 relative (norm-wise, SURVEY.md section 7 "mass scale") after 10
+steps.  The kernel uses rsqrt.approx (MUFU), FMA contraction and its own summation
+order, so it is not bit-exact against the CPU -- measured agreement is ~1e-6.
+"""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+KE_TOL = 1e-4
+POS_TOL = 1e-4
+
+
+def gpu_run(nbx, arrs, steps, **opts):
+    n = arrs[0].shape[0]
+    with nbx.Context(n) as c:
+        for k, v in opts.items():
+            c.set_option(k, v)
+        c.upload(*arrs)
+        ke, secs = c.run(steps)
+        out = c.state()
+        info = c.info()
+    return ke, out, info
+
+
+def test_c0_vs_oracle_and_fixture(nbx, oracle, golden, golden_c0_state):
+    arrs = nbx.ic(2000)
+    ke, out, info = gpu_run(nbx, arrs, 10)
+    s = oracle.ic_uniform(2000)
+    ke_o = oracle.run(s, 10, variant="ver2")
+    assert np.max(np.abs(ke - ke_o) / ke_o) < KE_TOL
+    want = np.array(golden["c0"]["kenergy_steps_1_10_ver2"])
+    assert np.max(np.abs(ke - want) / want) < KE_TOL
+    pos = np.stack(out[:3], axis=1)
+    vel = np.stack(out[3:], axis=1)
+    assert rel_l2(pos, s.pos()) < POS_TOL
+    assert rel_l2(vel, s.vel()) < 1e-4
+    gpos = np.stack([golden_c0_state[f] for f in ("px", "py", "pz")], axis=1)
+    assert rel_l2(pos, gpos) < POS_TOL
+    assert info["kernel_launches"] == 10
+
+
+def test_c0_full_run_matches_reference_table(nbx, golden):
+    arrs = nbx.ic(2000)
+    ke, _, _ = gpu_run(nbx, arrs, 500)
+    for row in golden["c0"]["cli_table_ver2"]:
+        got = ke[row["s"] - 1]
+        want = float(row["kenergy"])
+        assert abs(got - want) / want < 2e-4, row   # fixture has 5 significant digits
+
+
+def test_cli_is_a_drop_in(pkg, golden):
+    r = subprocess.run([pkg.CLI_PATH, "2000", "500"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    shape = golden["c0"]["cli_stdout_shape"]
+    # banner, header and rule lines are byte-identical to the reference's
+    assert lines[:6] == shape[:6]
+    rows = [l for l in lines if re.match(r"^ \d+", l)]
+    assert len(rows) == 10
+    for l, row in zip(rows, golden["c0"]["cli_table_ver2"]):
+        f = l.split()
+        assert int(f[0]) == row["s"] and f[1] == row["t"]
+        assert abs(float(f[2]) - float(row["kenergy"])) / float(row["kenergy"]) < 2e-4
+        assert float(f[3]) > 0 and float(f[4]) > 0
+        assert l.startswith(" " + str(row["s"]).ljust(8) + row["t"].ljust(8))
+    assert "# Number Threads     : 1" in lines
+    assert any(l.startswith("# Total Time (s)     : ") for l in lines)
+    assert any(l.startswith("# Average Perfomance : ") for l in lines)
+    assert "# Number GPUs        : 1" in lines
+    # argv rule of verN/main.cpp:36: a third argument disables the nSteps override
+    r2 = subprocess.run([pkg.CLI_PATH, "64", "7", "x"], capture_output=True, text=True, timeout=300)
+    assert " nPart = 64; nSteps = 500; dt = 0.1" in r2.stdout
+
+
+def test_cli_dump_matches_library(pkg, nbx, oracle, tmp_path):
+    dump = str(tmp_path / "d.bin")
+    env = dict(os.environ, NBODY_DUMP=dump, NBODY_SFREQ="5")
+    r = subprocess.run([pkg.CLI_PATH, "1000", "10"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    rows = [l for l in r.stdout.splitlines() if re.match(r"^ \d+", l)]
+    assert [int(l.split()[0]) for l in rows] == [5, 10]
+    s, ke, _, steps = oracle.read_dump(dump)
+    arrs = nbx.ic(1000)
+    ke2, out, _ = gpu_run(nbx, arrs, 10)
+    assert steps == 10 and np.float32(ke2[-1]) == ke
+    for a, f in zip(out, oracle.State.FIELDS):
+        assert np.array_equal(a, getattr(s, f)), f
+
+
+def test_c1_size_vs_threaded_oracle(nbx, oracle, golden):
+    n = 16384
+    arrs = nbx.ic(n)
+    ke, out, info = gpu_run(nbx, arrs, 10)
+    s = oracle.ic_uniform(n)
+    ke_o = oracle.run(s, 10, variant="ver7")
+    assert np.max(np.abs(ke - ke_o) / ke_o) < KE_TOL
+    assert rel_l2(np.stack(out[:3], axis=1), s.pos()) < POS_TOL
+    want = np.array(golden["c1"]["kenergy_steps_1_3_ver2"])
+    assert np.max(np.abs(ke[:3] - want) / want) < KE_TOL
+    assert info["j_splits"] > 1, "small N must use the j-split grid"
+
+
+def test_n65536_vs_reference_fixture(nbx, golden):
+    arrs = nbx.ic(65536)
+    ke, out, _ = gpu_run(nbx, arrs, 2)
+    want = np.array(golden["n65536"]["kenergy_steps_1_2_ver8"])
+    assert np.max(np.abs(ke - want) / want) < KE_TOL
+    for a, f in zip(out[:3], ("px", "py", "pz")):
+        assert abs(float(np.sum(a.astype(np.float64))) - golden["n65536"]["sum_after_2_ver8"][f]) < 0.05
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 100, 257, 1000, 2049, 5000])
+def test_ragged_and_tiny_sizes(nbx, oracle, n):
+    arrs = nbx.ic(n)
+    ke, out, _ = gpu_run(nbx, arrs, 5)
+    s = oracle.ic_uniform(n)
+    ke_o = oracle.run(s, 5, variant="ver2")
+    assert np.max(np.abs(ke - ke_o) / ke_o) < KE_TOL
+    assert rel_l2(np.stack(out[:3], axis=1), s.pos()) < POS_TOL
+    assert np.array_equal(out[0].shape, (n,))
+
+
+def test_zero_steps_and_state_roundtrip(nbx):
+    arrs = nbx.ic(1234)
+    ke, out, _ = gpu_run(nbx, arrs, 0)
+    assert ke.size == 0
+    for a, b in zip(out, arrs[:6]):
+        assert np.array_equal(a, b)   # upload -> pack -> unpack -> download is the identity
+
+
+def test_every_kernel_shape_agrees(nbx, oracle):
+    n = 3000
+    arrs = nbx.ic(n)
+    s = oracle.ic_uniform(n)
+    ke_o = oracle.run(s, 3, variant="ver2")
+    for v, name in enumerate(nbx.variant_names()):
+        ke, out, _ = gpu_run(nbx, arrs, 3, variant=v)
+        assert np.max(np.abs(ke - ke_o) / ke_o) < KE_TOL, name
+        assert rel_l2(np.stack(out[:3], axis=1), s.pos()) < POS_TOL, name
+
+
+@pytest.mark.parametrize("splits", [1, 2, 3, 7, 16, 61])
+def test_j_split_counts(nbx, oracle, splits):
+    n = 4096
+    arrs = nbx.ic(n)
+    ke, out, info = gpu_run(nbx, arrs, 3, j_splits=splits)
+    assert info["j_splits"] == splits
+    s = oracle.ic_uniform(n)
+    ke_o = oracle.run(s, 3, variant="ver2")
+    assert np.max(np.abs(ke - ke_o) / ke_o) < KE_TOL
+    assert rel_l2(np.stack(out[:3], axis=1), s.pos()) < POS_TOL
+
+
+def test_graph_replay_is_bitwise_identical_and_deterministic(nbx):
+    arrs = nbx.ic(4096)
+    ke_a, out_a, ia = gpu_run(nbx, arrs, 37, graph=1)
+    ke_b, out_b, ib = gpu_run(nbx, arrs, 37, graph=0)
+    ke_c, out_c, _ = gpu_run(nbx, arrs, 37, graph=1)
+    assert ia["use_graph"] == 1 and ib["use_graph"] == 0
+    assert ia["kernel_launches"] == 37 and ib["kernel_launches"] == 37
+    assert np.array_equal(ke_a, ke_b) and np.array_equal(ke_a, ke_c)
+    for a, b, c in zip(out_a, out_b, out_c):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_run_is_resumable(nbx):
+    # 10 steps == 4 steps + 6 steps on the same context (device-resident state)
+    arrs = nbx.ic(3000)
+    ke10, out10, _ = gpu_run(nbx, arrs, 10)
+    with nbx.Context(3000) as c:
+        c.upload(*arrs)
+        ke_a, _ = c.run(4)
+        ke_b, _ = c.run(6)
+        out = c.state()
+    assert np.array_equal(np.concatenate([ke_a, ke_b]), ke10)
+    for a, b in zip(out, out10):
+        assert np.array_equal(a, b)
+
+
+def test_simulate_one_call(nbx):
+    arrs = nbx.ic(2500)
+    ke_ref, out_ref, _ = gpu_run(nbx, arrs, 4)
+    work = [a.copy() for a in arrs]
+    ke, secs = nbx.simulate(4, *work)
+    assert np.array_equal(ke, ke_ref) and secs > 0
+    for a, b in zip(work[:6], out_ref):
+        assert np.array_equal(a, b)
+
+
+def test_accelerations_vs_fp64_truth(nbx, oracle):
+    n = 65536
+    arrs = nbx.ic(n)
+    with nbx.Context(n) as c:
+        c.upload(*arrs)
+        acc = c.accelerations()
+    s = oracle.ic_uniform(n)
+    sel = np.random.default_rng(1).choice(n, 2048, replace=False).astype(np.int32)
+    truth = oracle.acc_fp64(s, sel)
+    err = np.linalg.norm(acc[sel] - truth, axis=1) / np.linalg.norm(truth, axis=1)
+    assert np.max(err) < 1e-4 and np.median(err) < 5e-6
+
+
+def test_i_sharding_is_exact_on_one_gpu(nbx):
+    # the multi-GPU decomposition: rank r of W computes the i-shard [r*N/W, (r+1)*N/W) against
+    # all j.  With the same j-split the per-body sums are the same instructions in the same
+    # order, so concatenated shards must equal the unsharded result bit for bit.
+    n = 8192
+    arrs = nbx.ic(n)
+    with nbx.Context(n) as c:
+        c.set_option("j_splits", 4)
+        c.upload(*arrs)
+        full = c.accelerations()
+    for world in (2, 4, 8):
+        parts = []
+        for r in range(world):
+            with nbx.Context(n, rank=r, world=world) as c:
+                c.set_option("j_splits", 4)
+                c.upload(*arrs)
+                parts.append(c.accelerations())
+        assert np.array_equal(np.concatenate(parts)[:n], full[:n]), world
+
+
+def test_plummer_config_vs_oracle(nbx, oracle):
+    n = 8192
+    arrs = nbx.ic(n, "plummer")
+    ke, out, _ = gpu_run(nbx, arrs, 10)
+    s = oracle.State(n)
+    for f, a in zip(oracle.State.FIELDS, arrs):
+        setattr(s, f, a.copy())
+    ke_o = oracle.run(s, 10, variant="ver7")
+    assert np.max(np.abs(ke - ke_o) / ke_o) < KE_TOL
+    assert rel_l2(np.stack(out[:3], axis=1), s.pos()) < POS_TOL
+
+
+def test_full_size_c2_properties(nbx, oracle):
+    """N = 1,048,576 (BASELINE config 2): the CPU cannot finish a step in seconds, so check
+    properties: sampled accelerations against fp64 truth, kenergy against an fp64 sum of the
+    downloaded velocities, and the Euler identities r' = r + v' dt, v' = v + a dt."""
+    n = 1 << 20
+    arrs = nbx.ic(n)
+    with nbx.Context(n) as c:
+        c.upload(*arrs)
+        acc = c.accelerations()
+        ke, secs = c.run(1)
+        out = c.state()
+    s = oracle.State(n)
+    for f, a in zip(oracle.State.FIELDS, arrs):
+        setattr(s, f, a)
+    sel = np.random.default_rng(7).choice(n, 512, replace=False).astype(np.int32)
+    truth = oracle.acc_fp64(s, sel)
+    err = np.linalg.norm(acc[sel] - truth, axis=1) / np.linalg.norm(truth, axis=1)
+    assert np.max(err) < 1e-4
+    dt = np.float32(0.1)
+    for k in range(3):
+        v_new = arrs[3 + k] + acc[:, k] * dt
+        assert np.allclose(out[3 + k], v_new, rtol=1e-6, atol=1e-9)
+        assert np.allclose(out[k], arrs[k] + out[3 + k] * dt, rtol=1e-6, atol=1e-9)
+    s2 = oracle.State(n)
+    s2.vx, s2.vy, s2.vz, s2.mass = out[3], out[4], out[5], arrs[6]
+    ke64 = oracle.kenergy_fp64(s2)
+    assert abs(ke[0] - ke64) / ke64 < 1e-6
+    assert secs > 0

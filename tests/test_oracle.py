@@ -1,0 +1,112 @@
+"""CPU suite, part 1: the oracle is pinned.
+
+The oracle (oracle/nbody_oracle.c) is checked against (a) the committed fixtures that
+tests/golden/make_golden.py generated from the compiled, unmodified reference and
+(b) -- where /root/reference exists, i.e. in the build container -- the compiled
+reference itself, bit for bit for ver0 and ver2.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+HAVE_REF = os.path.isdir("/root/reference")
+
+
+def test_ic_matches_reference_fixture(oracle, golden):
+    for n_str, fx in golden["ic"].items():
+        n = int(n_str)
+        s = oracle.ic_uniform(n)
+        for f in oracle.State.FIELDS:
+            got = getattr(s, f)
+            assert [float("%.9g" % v) for v in got[:6]] == fx["head"][f], (n, f)
+            assert float(np.sum(got.astype(np.float64))) == fx["sum"][f], (n, f)
+
+
+def test_ic_known_first_draws(oracle):
+    # first draws of libstdc++'s uniform_real_distribution<float> on mt19937(42)
+    s = oracle.ic_uniform(8)
+    assert np.float32(s.px[0]) == np.float32(0.37454012)
+    assert np.float32(s.py[0]) == np.float32(0.796543002)
+    assert np.float32(s.pz[0]) == np.float32(0.95071429)
+    assert np.float32(s.vx[0]) == np.float32(-0.00025091978)
+    assert np.float32(s.mass[0]) == np.float32(8 * 0.37454012)
+
+
+@pytest.mark.parametrize("variant", ["ver0", "ver2"])
+def test_serial_oracle_bit_exact_vs_fixture(oracle, golden, golden_c0_state, variant):
+    s = oracle.ic_uniform(2000)
+    ke = oracle.run(s, 10, variant=variant)
+    want = golden["c0"]["kenergy_steps_1_10_" + variant]
+    assert [float("%.9g" % k) for k in ke] == want
+    sums = golden["c0"]["sum_after_10_" + variant]
+    for f in oracle.State.FIELDS:
+        assert float(np.sum(getattr(s, f).astype(np.float64))) == sums[f], f
+    if variant == "ver2":
+        for f in oracle.State.FIELDS:
+            assert np.array_equal(getattr(s, f), golden_c0_state[f]), f
+
+
+def test_threaded_oracle_close_to_reference_versions(oracle, golden):
+    # ver7/ver8 reorder the sums (simd lanes, threads): the reference's own spread is ~1e-6
+    s = oracle.ic_uniform(2000)
+    ke = oracle.run(s, 10, variant="ver7")
+    for ver in ("ver2", "ver7", "ver8"):
+        want = np.array(golden["c0"]["kenergy_steps_1_10_" + ver])
+        assert np.max(np.abs(ke - want) / want) < 3e-6, ver
+    s = oracle.ic_uniform(16384)
+    ke = oracle.run(s, 3, variant="ver7")
+    for ver in ("ver2", "ver7", "ver8"):
+        want = np.array(golden["c1"]["kenergy_steps_1_3_" + ver])
+        assert np.max(np.abs(ke - want) / want) < 5e-6, ver
+    for f in ("px", "py", "pz"):
+        assert abs(float(np.sum(getattr(s, f).astype(np.float64))) - golden["c1"]["sum_after_3_ver2"][f]) < 1e-4
+
+
+def test_cli_table_fixture_is_version_independent(golden):
+    # the 5-digit kenergy column is identical for every reference version
+    base = [r["kenergy"] for r in golden["c0"]["cli_table_ver2"]]
+    assert base == ["0.1432", "2.4341", "8.1256", "17.877", "32.966", "55.786", "91.132", "150.12", "264.78", "571.53"]
+    for ver in ("ver0", "ver5", "ver7", "ver8"):
+        assert [r["kenergy"] for r in golden["c0"]["cli_table_" + ver]] == base, ver
+
+
+def test_fp64_truth_agrees_with_float_oracle(oracle):
+    s = oracle.ic_uniform(4096)
+    sel = np.arange(0, 4096, 37, dtype=np.int32)
+    a64 = oracle.acc_fp64(s, sel)
+    s1 = s.copy()
+    oracle.run(s1, 1, variant="ver2")
+    a32 = (s1.vel()[sel].astype(np.float64) - s.vel()[sel].astype(np.float64)) / np.float64(np.float32(0.1))
+    # v' = v + a*dt in float: recovering a loses digits to v's ulp; compare norm-wise
+    assert rel_l2(a32, a64) < 2e-3
+    ke = oracle.kenergy_fp64(s1)
+    ke32 = oracle.run(s.copy(), 1, variant="ver2")[0]
+    assert abs(ke - ke32) / ke < 1e-5
+
+
+def test_flop_convention(oracle):
+    # ver0/GSimulation.cpp:122
+    assert oracle.gflop_per_step(2000) == pytest.approx(1e-9 * (29 * 2000.0 ** 2 + 19 * 2000.0))
+
+
+def test_edge_sizes(oracle):
+    for n in (1, 2, 3, 9):
+        s = oracle.ic_uniform(n)
+        ke = oracle.run(s, 2, variant="ver2")
+        assert np.all(np.isfinite(ke)) and np.all(np.isfinite(s.pos()))
+    s = oracle.ic_uniform(5)
+    assert oracle.run(s, 0).size == 0
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("variant,n,steps", [("ver0", 2000, 3), ("ver2", 2000, 3), ("ver2", 777, 5), ("ver0", 64, 20)])
+def test_oracle_bit_exact_vs_compiled_reference(oracle, variant, n, steps):
+    ref, ke_ref, _ = oracle.ref_run(variant, n, steps)
+    s = oracle.ic_uniform(n)
+    ke = oracle.run(s, steps, variant=variant)
+    assert ke[-1] == ke_ref
+    for f in oracle.State.FIELDS:
+        assert np.array_equal(getattr(s, f), getattr(ref, f)), f
