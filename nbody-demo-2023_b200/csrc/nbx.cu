@@ -107,11 +107,11 @@ struct Variant {
     const void *fn;
 };
 
-template <int R2, int THREADS, int TJ, int STAGES, int UNROLL, int MINB>
+template <int R2, int THREADS, int TJ, int STAGES, int UNROLL, int MINB, int MATH = 0>
 static Variant make_variant(const char *name)
 {
     return Variant{name, R2, THREADS, TJ, STAGES, UNROLL, MINB, nbx::step_smem_bytes<THREADS, TJ, STAGES>(),
-                   (const void *)nbx::step_kernel<R2, THREADS, TJ, STAGES, UNROLL, MINB>};
+                   (const void *)nbx::step_kernel<R2, THREADS, TJ, STAGES, UNROLL, MINB, MATH>};
 }
 
 static const std::vector<Variant> &variants()
@@ -129,6 +129,12 @@ static const std::vector<Variant> &variants()
         make_variant<1, 128, 256, 4, 4, 6>("r2_t128_u4"),
         make_variant<2, 512, 512, 4, 2, 1>("r4_t512_u2"),
         make_variant<2, 64, 128, 4, 2, 8>("r4_t64_u2"),
+        make_variant<2, 256, 256, 4, 2, 2, 1>("r4_t256_u2_sacc"),
+        make_variant<2, 256, 256, 4, 1, 2, 1>("r4_t256_u1_sacc"),
+        make_variant<3, 256, 256, 4, 1, 2, 1>("r6_t256_u1_sacc"),
+        make_variant<4, 256, 256, 4, 1, 1, 1>("r8_t256_u1_sacc"),
+        make_variant<2, 128, 256, 4, 2, 4, 1>("r4_t128_u2_sacc"),
+        make_variant<2, 256, 256, 4, 2, 2, 2>("probe_nomufu_r4_t256_u2"),
     };
     return v;
 }
@@ -584,12 +590,11 @@ int nbx_run_group(nbx_ctx **ctxs, int count, int nsteps, double *kenergy_out, do
         CU(cudaEventRecord(ctxs[g]->ev0, ctxs[g]->stream));
     }
     const bool nccl_x = count > 1 && ctxs[0]->exchange == NBX_EXCHANGE_NCCL;
-    if (!nccl_x) {
-        for (int g = 0; g < count; ++g) {
-            CU(cudaSetDevice(ctxs[g]->device));
-            if ((rc = enqueue_steps(ctxs[g], nsteps))) return rc;
-        }
+    if (count == 1) {
+        if ((rc = enqueue_steps(ctxs[0], nsteps))) return rc;
     } else {
+        // step-major order: with the P2P exchange a GPU's step s+1 spins until every peer has
+        // finished step s, so no GPU may be queued far ahead of the others by this one thread.
         for (int s = 0; s < nsteps; ++s) {
             for (int g = 0; g < count; ++g) {
                 nbx_ctx *c = ctxs[g];
@@ -597,13 +602,15 @@ int nbx_run_group(nbx_ctx **ctxs, int count, int nsteps, double *kenergy_out, do
                 if ((rc = launch_step(c, c->cur))) return rc;
                 c->cur ^= 1;
             }
-            NC(g_nccl.GroupStart());
-            for (int g = 0; g < count; ++g) {
-                nbx_ctx *c = ctxs[g];
-                float4 *buf = c->pos[c->cur];
-                NC(g_nccl.AllGather(buf + c->i_begin, buf, (size_t)c->i_count * 4, ncclFloat, c->comm, c->stream));
+            if (nccl_x) {
+                NC(g_nccl.GroupStart());
+                for (int g = 0; g < count; ++g) {
+                    nbx_ctx *c = ctxs[g];
+                    float4 *buf = c->pos[c->cur];
+                    NC(g_nccl.AllGather(buf + c->i_begin, buf, (size_t)c->i_count * 4, ncclFloat, c->comm, c->stream));
+                }
+                NC(g_nccl.GroupEnd());
             }
-            NC(g_nccl.GroupEnd());
         }
     }
     std::vector<double> tmp((size_t)std::max(nsteps, 1));

@@ -132,7 +132,7 @@ constexpr int step_smem_bytes()
 //    MINB    __launch_bounds__ min CTAs per SM
 //  grid = (i_tiles, j_splits)
 // ------------------------------------------------------------------------------
-template <int R2, int THREADS, int TJ, int STAGES, int UNROLL, int MINB>
+template <int R2, int THREADS, int TJ, int STAGES, int UNROLL, int MINB, int MATH = 0>
 __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_constant__ StepParams p)
 {
     constexpr int R = 2 * R2;
@@ -236,13 +236,24 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                     float2 r2 = __ffma2_rn(dx, dx, eps2v);
                     r2 = __ffma2_rn(dy, dy, r2);
                     r2 = __ffma2_rn(dz, dz, r2);
-                    const float2 inv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+                    // MATH == 2 is a timing probe only (no MUFU, wrong physics): what the MUFU costs the FMA pipe
+                    const float2 inv = (MATH == 2) ? __fmul2_rn(r2, eps2v)
+                                                   : make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
                     const float2 inv2 = __fmul2_rn(inv, inv);
                     const float2 mi = __fmul2_rn(mj, inv);
                     const float2 s = __fmul2_rn(inv2, mi);
-                    ax[b] = __ffma2_rn(dx, s, ax[b]);
-                    ay[b] = __ffma2_rn(dy, s, ay[b]);
-                    az[b] = __ffma2_rn(dz, s, az[b]);
+                    if (MATH != 1) {
+                        ax[b] = __ffma2_rn(dx, s, ax[b]);
+                        ay[b] = __ffma2_rn(dy, s, ay[b]);
+                        az[b] = __ffma2_rn(dz, s, az[b]);
+                    } else {
+                        // A packed FMA with three distinct 64-bit register operands issues at half
+                        // rate on sm_100a (tools/ubench2.cu: 4 cycles instead of 2); the scalar
+                        // form does not, so the accumulation -- the only 3-operand op -- is scalar.
+                        ax[b].x = fmaf(dx.x, s.x, ax[b].x); ax[b].y = fmaf(dx.y, s.y, ax[b].y);
+                        ay[b].x = fmaf(dy.x, s.x, ay[b].x); ay[b].y = fmaf(dy.y, s.y, ay[b].y);
+                        az[b].x = fmaf(dz.x, s.x, az[b].x); az[b].y = fmaf(dz.y, s.y, az[b].y);
+                    }
                 }
             }
         }

@@ -1,0 +1,121 @@
+"""GPU suite, multi-GPU part (skipped on a 1-GPU box): i-sharded runs against the single-GPU
+run.  With the j-split count pinned, every body's force is the same instruction sequence on
+any rank, so positions and velocities must agree BIT FOR BIT; kinetic energy is a sum of
+per-shard sums and may differ in the last bits."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu(nbx):
+    return nbx.device_count()
+
+
+def _single(nbx, arrs, steps, splits):
+    with nbx.Context(arrs[0].shape[0]) as c:
+        c.set_option("j_splits", splits)
+        c.set_option("graph", 0)
+        c.upload(*arrs)
+        ke, _ = c.run(steps)
+        return ke, c.state()
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_one_process_group_matches_single_gpu(nbx, world, exchange):
+    if _ngpu(nbx) < world:
+        pytest.skip(f"needs {world} GPUs")
+    n, steps, splits = 6000, 6, 3
+    arrs = nbx.ic(n)
+    ke1, st1 = _single(nbx, arrs, steps, splits)
+    ctxs = [nbx.Context(n, device=g, rank=g, world=world) for g in range(world)]
+    try:
+        for c in ctxs:
+            c.set_option("j_splits", splits)
+            c.set_option("exchange", nbx.EXCHANGE_P2P if exchange == "p2p" else nbx.EXCHANGE_NCCL)
+            c.upload(*arrs)
+        nbx.comm_init_all(ctxs)
+        if exchange == "p2p":
+            blobs = b"".join(c.p2p_export() for c in ctxs)
+            for c in ctxs:
+                c.p2p_attach(blobs)
+        ke, secs = nbx.run_group(ctxs, steps)
+        out = [np.zeros(n, dtype=np.float32) for _ in range(6)]
+        for c in ctxs:            # each rank fills positions (all) and its own velocity range
+            c.download(*out)
+        for a, b in zip(out, st1):
+            assert np.array_equal(a, b)
+        # every replica holds the same positions
+        for c in ctxs:
+            rep = c.state()
+            for a, b in zip(rep[:3], st1[:3]):
+                assert np.array_equal(a, b)
+        assert np.max(np.abs(ke - ke1) / ke1) < 1e-12
+        assert secs > 0
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_cli_multi_gpu(pkg, nbx):
+    if _ngpu(nbx) < 2:
+        pytest.skip("needs 2 GPUs")
+    outs = {}
+    for g, x in ((1, "nccl"), (2, "nccl"), (2, "p2p")):
+        env = dict(os.environ, NBODY_GPUS=str(g), NBODY_SFREQ="5", NBODY_EXCHANGE=x, NBODY_JSPLITS="2", NBODY_GRAPH="0")
+        r = subprocess.run([pkg.CLI_PATH, "4096", "10"], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs[(g, x)] = [l.split()[2] for l in r.stdout.splitlines() if re.match(r"^ \d+", l)]
+        assert f"# Number GPUs        : {g}" in r.stdout
+    assert outs[(1, "nccl")] == outs[(2, "nccl")] == outs[(2, "p2p")]
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_torchrun_two_ranks(nbx, exchange, tmp_path):
+    """One process per GPU, the way bench.py is launched: ranks step together and agree with
+    the single-GPU result."""
+    if _ngpu(nbx) < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "rank.py"
+    script.write_text(f"""
+import importlib, os, sys
+import numpy as np
+sys.path.insert(0, {REPO!r})
+import torch
+pkg = importlib.import_module("nbody-demo-2023_b200"); nbx = pkg.nbx
+dist = importlib.import_module("nbody-demo-2023_b200.dist")
+rank, local_rank, world = dist.init("nccl")
+n, steps = 5000, 5
+arrs = nbx.ic(n)
+ctx = dist.make_sharded_context(nbx, n, nbx.EXCHANGE_P2P if {exchange!r} == "p2p" else nbx.EXCHANGE_NCCL)
+ctx.set_option("j_splits", 2)
+ctx.upload(*arrs)
+dist.barrier()
+ke, secs = ctx.run(steps)
+st = ctx.state()
+i0, cnt = ctx.info()["i_begin"], ctx.info()["i_count"]
+np.savez({str(tmp_path)!r} + f"/rank{{rank}}.npz", ke=ke, px=st[0], py=st[1], pz=st[2], vx=st[3], i0=i0, cnt=cnt)
+dist.barrier()
+ctx.close()
+""")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    arrs = nbx.ic(5000)
+    ke1, st1 = _single(nbx, arrs, 5, 2)
+    for rank in (0, 1):
+        d = np.load(tmp_path / f"rank{rank}.npz")
+        assert np.max(np.abs(d["ke"] - ke1) / ke1) < 1e-12
+        for k, f in enumerate(("px", "py", "pz")):
+            assert np.array_equal(d[f], st1[k])
+        i0, cnt = int(d["i0"]), int(d["cnt"])
+        hi = min(i0 + cnt, 5000)
+        assert np.array_equal(d["vx"][i0:hi], st1[3][i0:hi])
