@@ -256,6 +256,8 @@ def main():
 
     if rank != 0:
         ctx.close()
+        if world > 1:
+            torch.distributed.destroy_process_group()
         return 0
 
     peaks, peak_kind = measured_peaks()
@@ -299,6 +301,8 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "G pair-interactions/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
     print(json.dumps(line), flush=True)
     ctx.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
     return 0
 
 

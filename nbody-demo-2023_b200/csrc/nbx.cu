@@ -199,8 +199,8 @@ static int resolve(nbx_ctx *c)
     c->i_tiles = (c->i_count + bi - 1) / bi;
 
     // j-split: equal CTAs quantise into waves of (SMs x resident CTAs); pick the split count
-    // whose last wave is fullest.  Keep >= 2 TMA tiles per split and prefer the smallest S
-    // within 1% of the best (fewer partials to park and combine).
+    // whose last wave is fullest.  Keep >= 2 TMA tiles per split and take a larger S only when
+    // it buys > 2% (each extra split parks and re-reads 16 B/body of partial forces).
     int splits = c->opt_splits;
     if (splits <= 0) {
         const double wave = (double)c->sm_count * occ;
@@ -210,7 +210,7 @@ static int resolve(nbx_ctx *c)
         for (int s = 1; s <= smax; ++s) {
             const double ctas = (double)c->i_tiles * s;
             const double eff = (ctas / wave) / std::ceil(ctas / wave);
-            if (eff > best + 0.01) { best = eff; splits = s; }
+            if (eff > best + 0.02) { best = eff; splits = s; }
         }
     }
     splits = std::max(1, std::min(splits, std::max(1, c->n_pad / 8)));
