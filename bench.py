@@ -279,7 +279,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "n_bodies": n, "pairs_per_step": pairs_per_step,
                    "parallelism": f"i-shard x{args.gpus}" + (f", exchange={args.exchange}" if args.gpus > 1 else ""),
-                   "kernel_shape": nbx.variant_names()[max(args.variant, 0)],
+                   "kernel_shape": nbx.variant_names()[info1["variant"]],
                    "i_tiles": info1["i_tiles"], "j_splits": info1["j_splits"], "ctas_per_sm": info1["ctas_per_sm"],
                    "l2": "flushed between timed steps (256 MiB memset); positions (16 B/body) are L2-resident by design within a step",
                    "timing": "CUDA events around each step on the launching stream (inside nbx_run), max over ranks; wall clock alongside"},

@@ -67,6 +67,7 @@ typedef struct nbx_info {
     int ctas_per_sm;        /* resident CTAs per SM (occupancy query)                 */
     int use_graph;          /* steps replayed from a CUDA graph                       */
     int exchange;           /* NBX_EXCHANGE_*                                         */
+    int variant;            /* kernel-shape index in use (after auto-selection)       */
     long long kernel_launches;   /* force-kernel launches since create                */
     long long aux_launches;      /* pack/unpack/other launches since create           */
     double last_run_seconds;     /* device time of the last nbx_run (CUDA events)     */
@@ -93,7 +94,7 @@ NBX_API void nbx_destroy(nbx_ctx *ctx);
  *   "j_splits"  >=1 force a j-split count, 0 = auto (fills the SMs at small N)
  *   "graph"     1/0 replay steps from a CUDA graph (auto: on for small N)
  *   "exchange"  NBX_EXCHANGE_*
- *   "variant"   index into the compiled kernel-shape table (see nbx_variant_name) */
+ *   "variant"   index into the compiled kernel-shape table (see nbx_variant_name), -1 = auto */
 NBX_API int nbx_set_option(nbx_ctx *ctx, const char *key, long long value);
 NBX_API int nbx_get_info(const nbx_ctx *ctx, nbx_info *out);
 NBX_API int nbx_variant_count(void);

@@ -117,27 +117,25 @@ static Variant make_variant(const char *name)
 static const std::vector<Variant> &variants()
 {
     static const std::vector<Variant> v = {
-        make_variant<2, 256, 256, 4, 2, 2>("r4_t256_u2"),   // default
+        make_variant<2, 256, 256, 4, 2, 2>("r4_t256_u2"),   // [0] default for large shards (kLargeVariant)
+        make_variant<1, 128, 256, 4, 4, 6>("r2_t128_u4"),   // [1] default for small shards (kSmallVariant)
+        make_variant<2, 256, 256, 4, 1, 2>("r4_t256_u1"),
         make_variant<2, 128, 256, 4, 2, 4>("r4_t128_u2"),
         make_variant<2, 256, 256, 4, 4, 2>("r4_t256_u4"),
-        make_variant<2, 256, 256, 4, 1, 2>("r4_t256_u1"),
         make_variant<3, 256, 256, 4, 2, 2>("r6_t256_u2"),
         make_variant<3, 128, 256, 4, 2, 4>("r6_t128_u2"),
         make_variant<4, 256, 256, 4, 1, 1>("r8_t256_u1"),
         make_variant<4, 128, 256, 4, 1, 3>("r8_t128_u1"),
         make_variant<1, 256, 256, 4, 4, 3>("r2_t256_u4"),
-        make_variant<1, 128, 256, 4, 4, 6>("r2_t128_u4"),
         make_variant<2, 512, 512, 4, 2, 1>("r4_t512_u2"),
         make_variant<2, 64, 128, 4, 2, 8>("r4_t64_u2"),
         make_variant<2, 256, 256, 4, 2, 2, 1>("r4_t256_u2_sacc"),
-        make_variant<2, 256, 256, 4, 1, 2, 1>("r4_t256_u1_sacc"),
-        make_variant<3, 256, 256, 4, 1, 2, 1>("r6_t256_u1_sacc"),
-        make_variant<4, 256, 256, 4, 1, 1, 1>("r8_t256_u1_sacc"),
-        make_variant<2, 128, 256, 4, 2, 4, 1>("r4_t128_u2_sacc"),
-        make_variant<2, 256, 256, 4, 2, 2, 2>("probe_nomufu_r4_t256_u2"),
     };
     return v;
 }
+
+constexpr int kLargeVariant = 0, kSmallVariant = 1;
+constexpr int kSmallShardBodies = 8192;   // below this the 256-body CTAs of kSmallVariant fill the SMs better
 
 // ------------------------------------------------------------------------------
 //  context
@@ -165,7 +163,7 @@ struct nbx_ctx {
     bool uploaded = false;
 
     // configuration
-    int variant = 0, opt_splits = 0, opt_graph = -1, exchange = NBX_EXCHANGE_NCCL;
+    int variant = 0, opt_variant = -1, opt_splits = 0, opt_graph = -1, exchange = NBX_EXCHANGE_NCCL;
     bool resolved = false;
     int i_tiles = 0, j_splits = 1, ctas_per_sm = 0, use_graph = 0;
 
@@ -188,6 +186,7 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static int resolve(nbx_ctx *c)
 {
     if (c->resolved) return NBX_OK;
+    c->variant = c->opt_variant >= 0 ? c->opt_variant : (c->i_count < kSmallShardBodies ? kSmallVariant : kLargeVariant);
     const Variant &v = variants()[c->variant];
     CU(cudaSetDevice(c->device));
     CU(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
@@ -198,19 +197,20 @@ static int resolve(nbx_ctx *c)
     const int bi = v.threads * v.r2 * 2;
     c->i_tiles = (c->i_count + bi - 1) / bi;
 
-    // j-split: equal CTAs quantise into waves of (SMs x resident CTAs); pick the split count
-    // whose last wave is fullest.  Keep >= 2 TMA tiles per split and take a larger S only when
-    // it buys > 2% (each extra split parks and re-reads 16 B/body of partial forces).
+    // j-split.  Equal CTAs are dealt round-robin to the SMs, so a step costs
+    //   ceil(i_tiles*S / SMs) rounds x (fixed cost per CTA + n_pad/S j-bodies) + S partials to combine.
+    // Fitted to same-box A/B runs (tools/ab.py; profiles/r01_ab_*.log): the fixed cost (prologue,
+    // first TMA round trip, epilogue) is worth ~48 j-bodies of a 1024-body CTA, a split ~2.
+    // N = 1 M: S = 13 (1% over S = 1); N = 65 536: S = 37; N = 16 384: S = 9.
     int splits = c->opt_splits;
     if (splits <= 0) {
-        const double wave = (double)c->sm_count * occ;
-        const int smax = std::max(1, std::min(64, c->n_pad / (2 * v.tj)));
-        double best = -1.0;
+        const int smax = std::max(1, std::min(64, c->n_pad / 128));
+        double best = 1e300;
         splits = 1;
         for (int s = 1; s <= smax; ++s) {
-            const double ctas = (double)c->i_tiles * s;
-            const double eff = (ctas / wave) / std::ceil(ctas / wave);
-            if (eff > best + 0.02) { best = eff; splits = s; }
+            const double rounds = std::ceil((double)c->i_tiles * s / c->sm_count);
+            const double cost = rounds * (48.0 + (double)c->n_pad / s) + 2.0 * s;
+            if (cost < best * 0.998) { best = cost; splits = s; }
         }
     }
     splits = std::max(1, std::min(splits, std::max(1, c->n_pad / 8)));
@@ -455,8 +455,8 @@ int nbx_set_option(nbx_ctx *c, const char *key, long long value)
         if (value != NBX_EXCHANGE_NCCL && value != NBX_EXCHANGE_P2P) return fail(NBX_ERR_ARG, "unknown exchange %lld", value);
         c->exchange = (int)value;
     } else if (k == "variant") {
-        if (value < 0 || value >= (long long)variants().size()) return fail(NBX_ERR_ARG, "variant out of range");
-        c->variant = (int)value;
+        if (value < -1 || value >= (long long)variants().size()) return fail(NBX_ERR_ARG, "variant out of range");
+        c->opt_variant = (int)value;
     } else {
         return fail(NBX_ERR_ARG, "unknown option '%s'", key);
     }
@@ -475,7 +475,7 @@ int nbx_get_info(const nbx_ctx *c, nbx_info *o)
     o->i_begin = c->i_begin; o->i_count = c->i_count;
     o->threads = v.threads; o->bodies_per_thread = 2 * v.r2; o->tile_bodies = v.tj; o->stages = v.stages;
     o->i_tiles = c->i_tiles; o->j_splits = c->j_splits; o->ctas_per_sm = c->ctas_per_sm;
-    o->use_graph = c->use_graph; o->exchange = c->exchange;
+    o->use_graph = c->use_graph; o->exchange = c->exchange; o->variant = c->variant;
     o->kernel_launches = c->kernel_launches; o->aux_launches = c->aux_launches;
     o->last_run_seconds = c->last_run_seconds; o->kernel_seconds_total = c->kernel_seconds_total;
     return NBX_OK;

@@ -236,20 +236,19 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                     float2 r2 = __ffma2_rn(dx, dx, eps2v);
                     r2 = __ffma2_rn(dy, dy, r2);
                     r2 = __ffma2_rn(dz, dz, r2);
-                    // MATH == 2 is a timing probe only (no MUFU, wrong physics): what the MUFU costs the FMA pipe
-                    const float2 inv = (MATH == 2) ? __fmul2_rn(r2, eps2v)
-                                                   : make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+                    const float2 inv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
                     const float2 inv2 = __fmul2_rn(inv, inv);
                     const float2 mi = __fmul2_rn(mj, inv);
                     const float2 s = __fmul2_rn(inv2, mi);
-                    if (MATH != 1) {
+                    if (MATH == 0) {
                         ax[b] = __ffma2_rn(dx, s, ax[b]);
                         ay[b] = __ffma2_rn(dy, s, ay[b]);
                         az[b] = __ffma2_rn(dz, s, az[b]);
                     } else {
-                        // A packed FMA with three distinct 64-bit register operands issues at half
-                        // rate on sm_100a (tools/ubench2.cu: 4 cycles instead of 2); the scalar
-                        // form does not, so the accumulation -- the only 3-operand op -- is scalar.
+                        // MATH 1 (kept for the record, not the default): a packed FMA with three
+                        // distinct 64-bit register operands issues at half rate in isolation
+                        // (tools/ubench2.cu), the scalar form does not -- yet in this loop the
+                        // all-packed form above is 2% faster (profiles/r01_sweep_n262144.log).
                         ax[b].x = fmaf(dx.x, s.x, ax[b].x); ax[b].y = fmaf(dx.y, s.y, ax[b].y);
                         ay[b].x = fmaf(dy.x, s.x, ay[b].x); ay[b].y = fmaf(dy.y, s.y, ay[b].y);
                         az[b].x = fmaf(dz.x, s.x, az[b].x); az[b].y = fmaf(dz.y, s.y, az[b].y);
@@ -295,6 +294,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll 8                                       // batch the L2 loads; the adds stay in split order
                     for (int s = 0; s < p.j_splits; ++s) {
                         const float4 v = __ldcg(&p.part[(size_t)s * p.i_count + 2 * ip + h]);
                         sx += v.x; sy += v.y; sz += v.z;

@@ -187,7 +187,7 @@ void GSimulation::start()
         std::cout << "# G pair-inter./s    : " << 1e-9 * pairs / devsecs << std::endl;
         std::cout << "# GFlops (20/pair)   : " << 20e-9 * pairs / devsecs << std::endl;
     }
-    std::cout << "# Kernel shape       : " << nbx_variant_name(env_int("NBODY_VARIANT", 0)) << ", " << info.i_tiles
+    std::cout << "# Kernel shape       : " << nbx_variant_name(info.variant) << ", " << info.i_tiles
               << " i-tiles x " << info.j_splits << " j-splits, graph=" << info.use_graph << std::endl;
 
     if (const char *dump = std::getenv("NBODY_DUMP")) {

@@ -14,14 +14,18 @@ nbx = pkg.nbx
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 splits_list = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
+only = sys.argv[4].split(",") if len(sys.argv) > 4 else None      # substrings of variant names
+graph = int(os.environ.get("SWEEP_GRAPH", "0"))
 arrs = nbx.ic(n)
 rows = []
 for v, name in enumerate(nbx.variant_names()):
+    if only and not any(o in name for o in only):
+        continue
     for sp in splits_list:
         with nbx.Context(n) as c:
             c.set_option("variant", v)
             c.set_option("j_splits", sp)
-            c.set_option("graph", 0)
+            c.set_option("graph", graph)
             c.upload(*arrs)
             c.run(1)
             best = 1e9
