@@ -123,6 +123,20 @@ def cpu_baseline_block(budget_s: float = 12.0):
                       f", N={n_s}, {steps} steps, {secs:.1f} s step-loop time, OMP_NUM_THREADS={cores}; pairs/s is flat in N for O(N^2)"}
 
 
+def gpu_reference_block():
+    """The reference's own (naive) CUDA backend on this GPU, for context: not the reference arm
+    (that is the CPU path) and never part of the product."""
+    from oracle import oracle as O
+    if not O.ref_cuda_available():
+        return None
+    n_s = 131072
+    rate, ke = O.ref_cuda_rate(n_s, 150)
+    return {"value": round(rate, 2), "unit": "G pair-interactions/s", "kind": "reference-cuda",
+            "sample": f"oracle/_ref/ver5_all_cuda (cuda/Compute.cu:31-66 unmodified, rebuilt -arch sm_100a, block 1024), "
+                      f"N={n_s}, 150 steps, its own timer over windows 2-3 (per-step H2D + kernel + D2H + host update)",
+            "kenergy_column": ke}
+
+
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -280,7 +294,7 @@ def main():
         "config": {"workload": wl["name"], "n_bodies": n, "pairs_per_step": pairs_per_step,
                    "parallelism": f"i-shard x{args.gpus}" + (f", exchange={args.exchange}" if args.gpus > 1 else ""),
                    "kernel_shape": nbx.variant_names()[info1["variant"]],
-                   "i_tiles": info1["i_tiles"], "j_splits": info1["j_splits"], "ctas_per_sm": info1["ctas_per_sm"],
+                   "i_tiles": info1["i_tiles"], "whole_tiles": info1["whole_tiles"], "j_splits": info1["j_splits"], "ctas_per_sm": info1["ctas_per_sm"],
                    "l2": "flushed between timed steps (256 MiB memset); positions (16 B/body) are L2-resident by design within a step",
                    "timing": "CUDA events around each step on the launching stream (inside nbx_run), max over ranks; wall clock alongside"},
         "gflops": round(FLOP_PER_PAIR * value, 1),
@@ -299,6 +313,11 @@ def main():
             line["cpu_baseline"] = cpu_baseline_block()
         except Exception as ex:   # the baseline is a report, not the product
             line["cpu_baseline"] = {"value": None, "unit": "G pair-interactions/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
+        try:
+            ctx.close()                      # free the GPU before the comparator runs on it
+            line["gpu_reference"] = gpu_reference_block()
+        except Exception as ex:
+            line["gpu_reference"] = {"value": None, "kind": "unavailable", "sample": repr(ex)}
     print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

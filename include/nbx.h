@@ -63,7 +63,8 @@ typedef struct nbx_info {
     int tile_bodies;        /* j-bodies per TMA stage                                 */
     int stages;             /* TMA ring depth                                         */
     int i_tiles;            /* CTAs along i                                           */
-    int j_splits;           /* CTAs along j (1 = no split)                            */
+    int whole_tiles;        /* leading i-tiles that run unsplit                       */
+    int j_splits;           /* j-split count of the remaining i-tiles (1 = none)      */
     int ctas_per_sm;        /* resident CTAs per SM (occupancy query)                 */
     int use_graph;          /* steps replayed from a CUDA graph                       */
     int exchange;           /* NBX_EXCHANGE_*                                         */

@@ -18,6 +18,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "libnbx.so")
 CLI_PATH = os.path.join(PKG_DIR, "nbody.x")
+CLI_ALL_PATH = os.path.join(PKG_DIR, "nbody_all.x")   # ver5_all-style argv
 
 
 def build(verbose: bool = False) -> None:
@@ -30,4 +31,4 @@ def build(verbose: bool = False) -> None:
 
 from . import nbx  # noqa: E402  (ctypes mirror; loading the .so is deferred to first use)
 
-__all__ = ["build", "nbx", "LIB_PATH", "CLI_PATH", "PKG_DIR", "REPO_DIR"]
+__all__ = ["build", "nbx", "LIB_PATH", "CLI_PATH", "CLI_ALL_PATH", "PKG_DIR", "REPO_DIR"]

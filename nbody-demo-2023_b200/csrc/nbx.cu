@@ -165,7 +165,7 @@ struct nbx_ctx {
     // configuration
     int variant = 0, opt_variant = -1, opt_splits = 0, opt_graph = -1, exchange = NBX_EXCHANGE_NCCL;
     bool resolved = false;
-    int i_tiles = 0, j_splits = 1, ctas_per_sm = 0, use_graph = 0;
+    int i_tiles = 0, whole_tiles = 0, j_splits = 1, split_bodies = 0, ctas_per_sm = 0, use_graph = 0;
 
     // graphs (2-step and 16-step replay units; both start and end on pos[0])
     cudaGraphExec_t graph2 = nullptr, graph16 = nullptr;
@@ -197,24 +197,33 @@ static int resolve(nbx_ctx *c)
     const int bi = v.threads * v.r2 * 2;
     c->i_tiles = (c->i_count + bi - 1) / bi;
 
-    // j-split.  Equal CTAs are dealt round-robin to the SMs, so a step costs
-    //   ceil(i_tiles*S / SMs) rounds x (fixed cost per CTA + n_pad/S j-bodies) + S partials to combine.
+    // j-split.  CTAs are dealt round-robin to the SMs, so a group of t equal tiles cut S ways costs
+    //   ceil(t*S / SMs) rounds x (fixed cost per CTA + n_pad/S j-bodies) + S partials to combine.
     // Fitted to same-box A/B runs (tools/ab.py; profiles/r01_ab_*.log): the fixed cost (prologue,
     // first TMA round trip, epilogue) is worth ~48 j-bodies of a 1024-body CTA, a split ~2.
-    // N = 1 M: S = 13 (1% over S = 1); N = 65 536: S = 37; N = 16 384: S = 9.
+    // Tiles that fill whole rounds of the SM count run unsplit (no partial-force traffic); only
+    // the tail -- everything, when there are fewer tiles than SMs -- is split.  A forced
+    // "j_splits" applies to every tile (that is what makes results shard-count independent).
     int splits = c->opt_splits;
+    c->whole_tiles = 0;
     if (splits <= 0) {
-        const int smax = std::max(1, std::min(64, c->n_pad / 128));
-        double best = 1e300;
+        c->whole_tiles = (c->i_tiles / c->sm_count) * c->sm_count;
+        const int tail = c->i_tiles - c->whole_tiles;
         splits = 1;
-        for (int s = 1; s <= smax; ++s) {
-            const double rounds = std::ceil((double)c->i_tiles * s / c->sm_count);
-            const double cost = rounds * (48.0 + (double)c->n_pad / s) + 2.0 * s;
-            if (cost < best * 0.998) { best = cost; splits = s; }
+        if (tail > 0) {
+            const int smax = std::max(1, std::min(64, c->n_pad / 128));
+            double best = 1e300;
+            for (int s = 1; s <= smax; ++s) {
+                const double rounds = std::ceil((double)tail * s / c->sm_count);
+                const double cost = rounds * (48.0 + (double)c->n_pad / s) + 2.0 * s;
+                if (cost < best * 0.998) { best = cost; splits = s; }
+            }
         }
     }
     splits = std::max(1, std::min(splits, std::max(1, c->n_pad / 8)));
     c->j_splits = splits;
+    if (splits == 1) c->whole_tiles = c->i_tiles;
+    c->split_bodies = std::max(0, c->i_count - c->whole_tiles * bi);
 
     if (c->opt_graph >= 0)
         c->use_graph = c->opt_graph;
@@ -225,9 +234,9 @@ static int resolve(nbx_ctx *c)
     if (c->part) { CU(cudaFree(c->part)); c->part = nullptr; }
     if (c->tile_ticket) { CU(cudaFree(c->tile_ticket)); c->tile_ticket = nullptr; }
     if (c->ke_part) { CU(cudaFree(c->ke_part)); c->ke_part = nullptr; }
-    if (splits > 1) CU(cudaMalloc(&c->part, (size_t)splits * c->i_count * sizeof(float4)));
-    CU(cudaMalloc(&c->tile_ticket, (size_t)c->i_tiles * sizeof(int)));
-    CU(cudaMemset(c->tile_ticket, 0, (size_t)c->i_tiles * sizeof(int)));
+    if (splits > 1) CU(cudaMalloc(&c->part, (size_t)splits * c->split_bodies * sizeof(float4)));
+    CU(cudaMalloc(&c->tile_ticket, (size_t)(c->i_tiles + 1) * sizeof(int)));
+    CU(cudaMemset(c->tile_ticket, 0, (size_t)(c->i_tiles + 1) * sizeof(int)));
     CU(cudaMalloc(&c->ke_part, (size_t)c->i_tiles * sizeof(double)));
     if (c->graph2) { cudaGraphExecDestroy(c->graph2); c->graph2 = nullptr; }
     if (c->graph16) { cudaGraphExecDestroy(c->graph16); c->graph16 = nullptr; }
@@ -252,7 +261,10 @@ static void fill_params(const nbx_ctx *c, StepParams &p, int in_buf, float4 *acc
     p.n_pad = c->n_pad;
     p.i_begin = c->i_begin;
     p.i_count = c->i_count;
+    p.i_tiles = c->i_tiles;
+    p.whole_tiles = c->whole_tiles;
     p.j_splits = c->j_splits;
+    p.split_bodies = c->split_bodies;
     p.dt = c->dt;
     p.eps2 = c->eps2;
     p.world = c->world;
@@ -273,7 +285,8 @@ static int launch_step(nbx_ctx *c, int in_buf, float4 *acc_out = nullptr)
     StepParams p;
     fill_params(c, p, in_buf, acc_out);
     void *args[] = {&p};
-    CU(cudaLaunchKernel(v.fn, dim3(c->i_tiles, c->j_splits), dim3(v.threads), args, v.smem, c->stream));
+    const int ctas = c->whole_tiles + (c->i_tiles - c->whole_tiles) * c->j_splits;
+    CU(cudaLaunchKernel(v.fn, dim3(ctas), dim3(v.threads), args, v.smem, c->stream));
     c->kernel_launches++;
     return NBX_OK;
 }
@@ -474,7 +487,7 @@ int nbx_get_info(const nbx_ctx *c, nbx_info *o)
     o->n = c->n; o->n_pad = c->n_pad; o->rank = c->rank; o->world = c->world;
     o->i_begin = c->i_begin; o->i_count = c->i_count;
     o->threads = v.threads; o->bodies_per_thread = 2 * v.r2; o->tile_bodies = v.tj; o->stages = v.stages;
-    o->i_tiles = c->i_tiles; o->j_splits = c->j_splits; o->ctas_per_sm = c->ctas_per_sm;
+    o->i_tiles = c->i_tiles; o->whole_tiles = c->whole_tiles; o->j_splits = c->j_splits; o->ctas_per_sm = c->ctas_per_sm;
     o->use_graph = c->use_graph; o->exchange = c->exchange; o->variant = c->variant;
     o->kernel_launches = c->kernel_launches; o->aux_launches = c->aux_launches;
     o->last_run_seconds = c->last_run_seconds; o->kernel_seconds_total = c->kernel_seconds_total;

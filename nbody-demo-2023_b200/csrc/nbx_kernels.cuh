@@ -19,8 +19,9 @@
 //   * the Euler update, the kinetic-energy reduction (deterministic: per-CTA partial,
 //     last CTA sums in tile order) and, on several GPUs, the NVLink stores of the
 //     updated records into every peer's replica all run in the same kernel's epilogue;
-//   * a j-split grid (gridDim.y) with a last-arriver combine in fixed split order
-//     fills the 148 SMs when N/BI CTAs would not.
+//   * a j-split with a last-arriver combine in fixed split order fills the 148 SMs: the first
+//     `whole_tiles` i-tiles (whole rounds of the SM count) run unsplit, the remaining tail tiles
+//     -- all tiles when there are fewer than SMs -- are cut `j_splits` ways along j.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -34,8 +35,8 @@ struct StepParams {
     const float4 *pos_in;   // pair-packed records, n_pad bodies = n_pad float4s
     float4 *pos_out;        // same layout, the other half of the ping-pong
     float4 *vel;            // shard-local: (vx, vy, vz, m) per body
-    float4 *part;           // [j_splits][i_count] partial accelerations
-    int *tile_ticket;       // [i_tiles] arrival counters (self-resetting)
+    float4 *part;           // [j_splits][split_bodies] partial accelerations of the split tiles
+    int *tile_ticket;       // [i_tiles - whole_tiles] arrival counters (self-resetting)
     double *ke_part;        // [i_tiles]
     int *ke_ticket;         // [1]
     double *ke_out;         // [steps] kinetic energy, slot = *dev_step
@@ -44,7 +45,10 @@ struct StepParams {
     float4 *acc_out;        // non-null: store accelerations, do not update (nbx_accelerations)
     int n_pad;
     int i_begin, i_count;
-    int j_splits;
+    int i_tiles;            // CTAs' worth of i-bodies in this shard
+    int whole_tiles;        // tiles [0, whole_tiles) are not split along j
+    int j_splits;           // split count of tiles [whole_tiles, i_tiles)
+    int split_bodies;       // i-bodies covered by split tiles (stride of `part`)
     float dt, eps2;
     // P2P exchange (world > 1 and exchange == P2P): peers' replicas and completion flags
     int world, rank, p2p;
@@ -130,7 +134,7 @@ constexpr int step_smem_bytes()
 //    STAGES  ring depth (>= 3: one being read, one landed, one in flight)
 //    UNROLL  j-records per inner-loop trip (1, 2 or 4)
 //    MINB    __launch_bounds__ min CTAs per SM
-//  grid = (i_tiles, j_splits)
+//  grid = whole_tiles + (i_tiles - whole_tiles) * j_splits CTAs, whole tiles first
 // ------------------------------------------------------------------------------
 template <int R2, int THREADS, int TJ, int STAGES, int UNROLL, int MINB, int MATH = 0>
 __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_constant__ StepParams p)
@@ -147,13 +151,18 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     int *s_flag = reinterpret_cast<int *>(red + WARPS);
 
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
-    const int split = blockIdx.y;
+    int tile = blockIdx.x, split = 0, nsplit = 1;
+    if (tile >= p.whole_tiles) {
+        const int r = tile - p.whole_tiles;
+        tile = p.whole_tiles + r / p.j_splits;
+        split = r % p.j_splits;
+        nsplit = p.j_splits;
+    }
 
     // ---- j range of this CTA, in 8-body chunks so every TMA copy is 128-byte granular
     const int chunks = p.n_pad >> 3;
-    const int jb = (int)(((long long)chunks * split) / p.j_splits) << 3;
-    const int je = (int)(((long long)chunks * (split + 1)) / p.j_splits) << 3;
+    const int jb = (int)(((long long)chunks * split) / nsplit) << 3;
+    const int je = (int)(((long long)chunks * (split + 1)) / nsplit) << 3;
     const int ntiles = (je - jb + TJ - 1) / TJ;
 
     if (tid == 0) {
@@ -270,8 +279,10 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     }
 
     // ---- j-split: park partials, the last CTA of this i-tile adds them in split order
-    if (p.j_splits > 1) {
-        float4 *mine = p.part + (size_t)split * p.i_count;
+    if (nsplit > 1) {
+        constexpr int BI = THREADS * R;
+        const int tb0 = p.whole_tiles * BI;                    // first body held in `part`
+        float4 *mine = p.part + (size_t)split * p.split_bodies - tb0;
 #pragma unroll
         for (int k = 0; k < R2; ++k) {
             const int ip = pair_base + k * THREADS;
@@ -282,11 +293,12 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         }
         __threadfence();
         __syncthreads();
-        if (tid == 0) *s_flag = (atomicAdd(&p.tile_ticket[tile], 1) == p.j_splits - 1);
+        int *ticket = &p.tile_ticket[tile - p.whole_tiles];
+        if (tid == 0) *s_flag = (atomicAdd(ticket, 1) == nsplit - 1);
         __syncthreads();
         if (!*s_flag) return;
         __threadfence();
-        if (tid == 0) p.tile_ticket[tile] = 0;
+        if (tid == 0) *ticket = 0;
 #pragma unroll
         for (int k = 0; k < R2; ++k) {
             const int ip = pair_base + k * THREADS;
@@ -295,8 +307,8 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                 for (int h = 0; h < 2; ++h) {
                     float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll 8                                       // batch the L2 loads; the adds stay in split order
-                    for (int s = 0; s < p.j_splits; ++s) {
-                        const float4 v = __ldcg(&p.part[(size_t)s * p.i_count + 2 * ip + h]);
+                    for (int s = 0; s < nsplit; ++s) {
+                        const float4 v = __ldcg(&p.part[(size_t)s * p.split_bodies + (2 * ip + h - tb0)]);
                         sx += v.x; sy += v.y; sz += v.z;
                     }
                     fx[2 * k + h] = sx; fy[2 * k + h] = sy; fz[2 * k + h] = sz;
@@ -351,13 +363,13 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         for (int w = 0; w < WARPS; ++w) s += red[w];
         p.ke_part[tile] = s;
         __threadfence();
-        *s_flag = (atomicAdd(p.ke_ticket, 1) == (int)gridDim.x - 1);
+        *s_flag = (atomicAdd(p.ke_ticket, 1) == p.i_tiles - 1);
     }
     __syncthreads();
     if (!*s_flag) return;
     __threadfence();
     double s = 0.0;
-    for (int i = tid; i < (int)gridDim.x; i += THREADS) s += __ldcg(&p.ke_part[i]);
+    for (int i = tid; i < p.i_tiles; i += THREADS) s += __ldcg(&p.ke_part[i]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     __syncthreads();

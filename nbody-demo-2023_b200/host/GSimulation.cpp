@@ -43,10 +43,14 @@ int env_int(const char *name, int dflt)
 
 }  // namespace
 
+bool GSimulation::s_banner = true;
+
 GSimulation::GSimulation() : particles(nullptr), _kenergy(0), _totTime(0), _totFlops(0), _ngpus(1), _ic("uniform")
 {
-    std::cout << "===============================" << std::endl;
-    std::cout << " Initialize Gravity Simulation" << std::endl;
+    if (s_banner) {
+        std::cout << "===============================" << std::endl;
+        std::cout << " Initialize Gravity Simulation" << std::endl;
+    }
     set_npart(2000);
     set_nsteps(500);
     set_tstep(0.1);
@@ -96,6 +100,21 @@ void GSimulation::start()
     init_acc();
     init_mass();
 
+    // ---- ver5_all knobs: a CPU share cannot be honoured (no CPU path here, by design)
+    if (_devices == 1 || _devices == 3) {
+        std::cerr << "nbody.x: device selector '" << (_devices == 1 ? "cpu" : "cpu+gpu")
+                  << "' asks for a CPU share; this backend is GPU-only (no CPU fallback)" << std::endl;
+        std::exit(1);
+    }
+    int forced_variant = -1;
+    if (_thread_dim0 != 0) {   // cuda/Compute.cu:137-145: block size from thread_dim0
+        const int want = _thread_dim0 >= 512 ? 512 : _thread_dim0 >= 256 ? 256 : _thread_dim0 >= 128 ? 128 : 64;
+        const std::string name = "r4_t" + std::to_string(want) + "_u2";
+        for (int v = 0; v < nbx_variant_count(); ++v)
+            if (name == nbx_variant_name(v)) forced_variant = v;
+        std::cout << "using block_size = " << want << std::endl;
+    }
+
     // ---- device set-up: outside the timed region, like the reference's allocation + init
     const int G = _ngpus < 1 ? 1 : _ngpus;
     const float softeningSquared = 1e-3f;   // ver2/GSimulation.cpp:114
@@ -105,6 +124,7 @@ void GSimulation::start()
     const long long exchange = (xch && std::strcmp(xch, "p2p") == 0) ? NBX_EXCHANGE_P2P : NBX_EXCHANGE_NCCL;
     for (int g = 0; g < G; ++g) {
         if (nbx_create(&ctx[g], n, g, g, G, get_tstep(), Gconst, softeningSquared)) die("nbx_create");
+        if (forced_variant >= 0 && nbx_set_option(ctx[g], "variant", forced_variant)) die("variant");
         if (std::getenv("NBODY_VARIANT") && nbx_set_option(ctx[g], "variant", env_int("NBODY_VARIANT", 0))) die("variant");
         if (std::getenv("NBODY_JSPLITS") && nbx_set_option(ctx[g], "j_splits", env_int("NBODY_JSPLITS", 0))) die("j_splits");
         if (std::getenv("NBODY_GRAPH") && nbx_set_option(ctx[g], "graph", env_int("NBODY_GRAPH", -1))) die("graph");
@@ -188,7 +208,8 @@ void GSimulation::start()
         std::cout << "# GFlops (20/pair)   : " << 20e-9 * pairs / devsecs << std::endl;
     }
     std::cout << "# Kernel shape       : " << nbx_variant_name(info.variant) << ", " << info.i_tiles
-              << " i-tiles x " << info.j_splits << " j-splits, graph=" << info.use_graph << std::endl;
+              << " i-tiles (" << info.whole_tiles << " whole, rest x " << info.j_splits << " j-splits), graph="
+              << info.use_graph << std::endl;
 
     if (const char *dump = std::getenv("NBODY_DUMP")) {
         ParticleSoA &p = *particles;

@@ -27,6 +27,14 @@ public:
     void set_number_of_steps(int N);
     void start();
 
+    // ver5_all surface (ver5_all/GSimulation.hpp:51-58), used by nbody_all.x
+    void set_devices(int N) { _devices = N; }          // 1 cpu, 2 gpu, 3 cpu+gpu
+    int get_devices() const { return _devices; }
+    void set_cpu_ratio(const float &r) { _cpu_ratio = r; }
+    void set_thread_dim0(const int &d) { _thread_dim0 = d; }
+    void set_thread_dim1(const int &d) { _thread_dim1 = d; }
+    static void set_banner(bool on) { s_banner = on; } // ver5_all prints the banner from main()
+
     // extensions (not in the reference; defaults keep `./nbody.x N S` identical)
     void set_number_of_gpus(int G) { _ngpus = G; }
     void set_sample_frequency(int sf) { if (sf > 0) _sfreq = sf; }
@@ -44,6 +52,9 @@ private:
     double _totFlops;  // total number of flops
     int _ngpus;
     std::string _ic;   // "uniform" (reference) or "plummer"
+    int _devices = 0, _thread_dim0 = 0, _thread_dim1 = 0;
+    float _cpu_ratio = -1.0f;
+    static bool s_banner;
 
     void init_pos();
     void init_vel();

@@ -39,7 +39,7 @@ class Info(C.Structure):
     _fields_ = [(k, C.c_int) for k in (
         "abi_version", "device", "sm_count", "sm_clock_khz", "n", "n_pad", "rank", "world",
         "i_begin", "i_count", "threads", "bodies_per_thread", "tile_bodies", "stages",
-        "i_tiles", "j_splits", "ctas_per_sm", "use_graph", "exchange", "variant")] + [
+        "i_tiles", "whole_tiles", "j_splits", "ctas_per_sm", "use_graph", "exchange", "variant")] + [
         ("kernel_launches", C.c_longlong), ("aux_launches", C.c_longlong),
         ("last_run_seconds", C.c_double), ("kernel_seconds_total", C.c_double)]
 

@@ -152,3 +152,23 @@ def ref_run(ver: str, n: int, nsteps: int, threads: int | None = None):
                        stdout=subprocess.DEVNULL)
         s, ke, secs, _ = read_dump(out)
     return s, ke, secs
+
+
+def ref_cuda_available() -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "ver5_all_cuda", "nbody.x"))
+
+
+def ref_cuda_rate(n: int, steps: int = 150):
+    """Run the reference's own CUDA backend (ver5_all/programming_models/cuda/Compute.cu, unmodified,
+    rebuilt for sm_100a) through its CLI and return (G pairs/s, kenergy column) from its own table:
+    windows after the first (the first window carries CUDA context creation).  Its timer brackets
+    the per-step H2D + kernel + D2H + host Euler/energy loop (cuda/Compute.cu:150-194)."""
+    import re
+    exe = os.path.join(REF_DIR, "ver5_all_cuda", "nbody.x")
+    out = subprocess.run([exe, str(n), str(steps), "gpu"], check=True, capture_output=True, text=True).stdout
+    rows = [l.split() for l in out.splitlines() if re.match(r"^ \d+\s", l)]
+    if len(rows) < 2:
+        raise RuntimeError("reference CUDA backend printed fewer than 2 table rows")
+    secs = sum(float(r[3]) for r in rows[1:])
+    nsteps = 50 * (len(rows) - 1)
+    return float(n) * float(n) * nsteps / secs / 1e9, [r[2] for r in rows]

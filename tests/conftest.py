@@ -40,7 +40,7 @@ def oracle():
 def pkg():
     """The product package; builds libnbx.so / nbody.x in-tree if they are missing."""
     p = importlib.import_module("nbody-demo-2023_b200")
-    if not (os.path.exists(p.LIB_PATH) and os.path.exists(p.CLI_PATH)):
+    if not (os.path.exists(p.LIB_PATH) and os.path.exists(p.CLI_PATH) and os.path.exists(p.CLI_ALL_PATH)):
         p.build()
     return p
 

@@ -115,3 +115,9 @@ def test_fails_loudly_without_gpu(pkg, nbx):
     assert r.returncode == 1 and "no CUDA device" in r.stderr
     # the banner is printed by the constructor before start() fails, as in the reference
     assert r.stdout.splitlines()[:2] == ["===============================", " Initialize Gravity Simulation"]
+
+
+def test_ver5_all_cli_refuses_cpu_share(pkg):
+    r = subprocess.run([pkg.CLI_ALL_PATH, "64", "2", "cpu"], capture_output=True, text=True)
+    assert r.returncode == 1 and "GPU-only" in r.stderr
+    assert r.stdout.splitlines()[0] == "cpu"          # ver5_all/main.cpp:42 echoes the selector first

@@ -32,7 +32,7 @@ def _single(nbx, arrs, steps, splits):
 def test_one_process_group_matches_single_gpu(nbx, world, exchange):
     if _ngpu(nbx) < world:
         pytest.skip(f"needs {world} GPUs")
-    n, steps, splits = 6000, 6, 3
+    n, steps, splits = 6144, 6, 3      # multiple of 8*world for every world: same padding as 1 GPU
     arrs = nbx.ic(n)
     ke1, st1 = _single(nbx, arrs, steps, splits)
     ctxs = [nbx.Context(n, device=g, rank=g, world=world) for g in range(world)]

@@ -271,3 +271,47 @@ def test_full_size_c2_properties(nbx, oracle):
     ke64 = oracle.kenergy_fp64(s2)
     assert abs(ke[0] - ke64) / ke64 < 1e-6
     assert secs > 0
+
+
+def test_hybrid_whole_plus_split_tail(nbx, oracle):
+    """Auto decomposition at a size with more i-tiles than SMs: leading whole rounds of tiles run
+    unsplit, only the tail is cut along j.  Results must still match the oracle, and must equal
+    the all-unsplit run to rounding."""
+    n = 200 * 1024 + 333           # 201 tiles of 1024 bodies on a 148-SM part: 148 whole + 53 split
+    arrs = nbx.ic(n)
+    ke, out, info = gpu_run(nbx, arrs, 2)
+    assert 0 < info["whole_tiles"] < info["i_tiles"] and info["j_splits"] > 1
+    ke1, out1, info1 = gpu_run(nbx, arrs, 2, j_splits=1)
+    assert info1["whole_tiles"] == info1["i_tiles"]
+    assert np.max(np.abs(ke - ke1) / ke1) < 1e-6
+    assert rel_l2(np.stack(out[:3], axis=1), np.stack(out1[:3], axis=1)) < 1e-6
+    # whole tiles did not go through the split/combine path: bitwise equal to the unsplit run
+    w = info["whole_tiles"] * info["threads"] * info["bodies_per_thread"]
+    for a, b in zip(out, out1):
+        assert np.array_equal(a[:w], b[:w])
+    s = oracle.State(n)
+    for f, a in zip(oracle.State.FIELDS, arrs):
+        setattr(s, f, a.copy())
+    sel = np.random.default_rng(3).choice(n, 1024, replace=False).astype(np.int32)
+    with nbx.Context(n) as c:
+        c.upload(*arrs)
+        acc = c.accelerations()
+    truth = oracle.acc_fp64(s, sel)
+    err = np.linalg.norm(acc[sel] - truth, axis=1) / np.linalg.norm(truth, axis=1)
+    assert np.max(err) < 1e-4
+
+
+def test_ver5_all_style_cli(pkg, golden):
+    """nbody_all.x takes ver5_all/main.cpp's argv: nSteps whenever argc > 2, device string echoed
+    first, block size from argv[5]; a CPU share is refused loudly."""
+    r = subprocess.run([pkg.CLI_ALL_PATH, "2000", "100", "gpu", "0.5", "128", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == "gpu" and lines[2] == " Initialize Gravity Simulation"
+    assert "using block_size = 128" in lines
+    rows = [l.split() for l in lines if re.match(r"^ \d+", l)]
+    assert [int(x[0]) for x in rows] == [50, 100]
+    for x, row in zip(rows, golden["c0"]["cli_table_ver2"]):
+        assert abs(float(x[2]) - float(row["kenergy"])) / float(row["kenergy"]) < 2e-4
+    r = subprocess.run([pkg.CLI_ALL_PATH, "2000", "100", "cpu+gpu"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "GPU-only" in r.stderr

@@ -26,4 +26,4 @@ for r in range(reps):
         res[k].append(secs / steps)
 for k, v in sorted(res.items(), key=lambda kv: np.median(kv[1])):
     med = float(np.median(v)); info = ctxs[k].info()
-    print(f"{k[0]:16s} S={info['j_splits']:3d} tiles={info['i_tiles']:5d} med {med*1e3:9.4f} ms  min {min(v)*1e3:9.4f}  {float(n)*n/med/1e9:8.1f} Gpairs/s  {float(n)*n/med/1e9*20e-3/74.45*100:5.1f}% peak", flush=True)
+    print(f"{k[0]:16s} S={info['j_splits']:3d} tiles={info['i_tiles']:5d} whole={info['whole_tiles']:5d} med {med*1e3:9.4f} ms  min {min(v)*1e3:9.4f}  {float(n)*n/med/1e9:8.1f} Gpairs/s  {float(n)*n/med/1e9*20e-3/74.45*100:5.1f}% peak", flush=True)

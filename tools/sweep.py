@@ -36,7 +36,7 @@ for v, name in enumerate(nbx.variant_names()):
         rate = float(n) * n / best / 1e9
         rows.append(dict(variant=name, n=n, j_splits=info["j_splits"], i_tiles=info["i_tiles"],
                          ctas_per_sm=info["ctas_per_sm"], ms=best * 1e3, gpairs=rate, tflops20=rate * 20e-3))
-        print(f"{name:14s} N={n} tiles={info['i_tiles']:5d} splits={info['j_splits']:3d} occ={info['ctas_per_sm']} "
+        print(f"{name:14s} N={n} tiles={info['i_tiles']:5d} whole={info['whole_tiles']:5d} splits={info['j_splits']:3d} occ={info['ctas_per_sm']} "
               f"{best*1e3:9.3f} ms  {rate:8.1f} Gpairs/s  {rate*20e-3:6.2f} TF(20)  {rate*20e-3/74.5*100:5.1f}% peak", flush=True)
 os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
 with open(os.path.join(REPO, "gpurun_out", f"sweep_{n}.json"), "w") as f:
