@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS))
-    ap.add_argument("--exchange", default="p2p", choices=["nccl", "p2p"])
+    ap.add_argument("--exchange", default="p2p", choices=["nccl", "nccl_overlap", "p2p"])
     ap.add_argument("--variant", type=int, default=-1)
     ap.add_argument("--j-splits", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -205,7 +205,7 @@ def main():
         h[:] = a
     out = [nbx.pinned_empty(n) for _ in range(6)]
 
-    exchange = nbx.EXCHANGE_P2P if args.exchange == "p2p" else nbx.EXCHANGE_NCCL
+    exchange = {"p2p": nbx.EXCHANGE_P2P, "nccl": nbx.EXCHANGE_NCCL, "nccl_overlap": nbx.EXCHANGE_NCCL_OVERLAP}[args.exchange]
     ctx = dist.make_sharded_context(nbx, n, exchange, device=local_rank)
     if args.variant >= 0:
         ctx.set_option("variant", args.variant)

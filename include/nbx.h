@@ -45,8 +45,10 @@ enum {
 /* How updated positions reach the other GPUs after each step (multi-GPU only). */
 enum {
     NBX_EXCHANGE_NCCL = 0, /* ncclAllGather of the updated shard (stream ordered)          */
-    NBX_EXCHANGE_P2P = 1   /* the force kernel's epilogue stores each updated body straight
+    NBX_EXCHANGE_P2P = 1,  /* the force kernel's epilogue stores each updated body straight
                               into every peer's replica over NVLink; flags replace the collective */
+    NBX_EXCHANGE_NCCL_OVERLAP = 2 /* ncclAllGather on a side stream, hidden behind the next step's
+                              force work on the rank's own j-shard (a step = two launches)   */
 };
 
 typedef struct nbx_info {

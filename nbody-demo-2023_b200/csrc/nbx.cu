@@ -171,6 +171,10 @@ struct nbx_ctx {
     cudaGraphExec_t graph2 = nullptr, graph16 = nullptr;
 
     // multi-GPU
+    cudaStream_t comm_stream = nullptr;          // NCCL-overlap mode: all-gathers run here
+    cudaEvent_t ev_step = nullptr, ev_gather = nullptr;
+    bool gather_pending = false;
+    int s_local = 1, s_remote = 1;               // NCCL-overlap mode: j-splits of the two launches
     ncclComm_t comm = nullptr;
     bool p2p_ready = false;
     float4 *peer_pos[2][nbx::kMaxWorld] = {};
@@ -182,6 +186,20 @@ struct nbx_ctx {
 };
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// j-split count for `tiles` equal i-tiles sweeping `j_len` j-bodies on `sms` SMs (cost model below).
+static int pick_splits(int tiles, int j_len, int sms)
+{
+    const int smax = std::max(1, std::min(64, j_len / 128));
+    double best = 1e300;
+    int splits = 1;
+    for (int s = 1; s <= smax; ++s) {
+        const double rounds = std::ceil((double)tiles * s / sms);
+        const double cost = rounds * (48.0 + (double)j_len / s) + 2.0 * s;
+        if (cost < best * 0.998) { best = cost; splits = s; }
+    }
+    return splits;
+}
 
 static int resolve(nbx_ctx *c)
 {
@@ -206,19 +224,18 @@ static int resolve(nbx_ctx *c)
     // "j_splits" applies to every tile (that is what makes results shard-count independent).
     int splits = c->opt_splits;
     c->whole_tiles = 0;
-    if (splits <= 0) {
+    const bool overlap = c->world > 1 && c->exchange == NBX_EXCHANGE_NCCL_OVERLAP;
+    if (overlap) {
+        // a step is two launches: the own j-shard (no remote data needed), then the other shards
+        // once their all-gather has landed; every tile is split, partials of both launches meet
+        // in the last-arriver combine of the second one.
+        c->s_local = splits > 0 ? splits : pick_splits(c->i_tiles, c->i_count, c->sm_count);
+        c->s_remote = splits > 0 ? splits : pick_splits(c->i_tiles, c->n_pad - c->i_count, c->sm_count);
+        splits = c->s_local + c->s_remote;
+    } else if (splits <= 0) {
         c->whole_tiles = (c->i_tiles / c->sm_count) * c->sm_count;
         const int tail = c->i_tiles - c->whole_tiles;
-        splits = 1;
-        if (tail > 0) {
-            const int smax = std::max(1, std::min(64, c->n_pad / 128));
-            double best = 1e300;
-            for (int s = 1; s <= smax; ++s) {
-                const double rounds = std::ceil((double)tail * s / c->sm_count);
-                const double cost = rounds * (48.0 + (double)c->n_pad / s) + 2.0 * s;
-                if (cost < best * 0.998) { best = cost; splits = s; }
-            }
-        }
+        splits = tail > 0 ? pick_splits(tail, c->n_pad, c->sm_count) : 1;
     }
     splits = std::max(1, std::min(splits, std::max(1, c->n_pad / 8)));
     c->j_splits = splits;
@@ -229,7 +246,7 @@ static int resolve(nbx_ctx *c)
         c->use_graph = c->opt_graph;
     else   // launch latency matters below ~1 ms per step
         c->use_graph = ((double)c->n_pad * (double)c->i_count < 2.5e9) ? 1 : 0;
-    if (c->world > 1 && c->exchange == NBX_EXCHANGE_NCCL) c->use_graph = 0;
+    if (c->world > 1 && c->exchange != NBX_EXCHANGE_P2P) c->use_graph = 0;
 
     if (c->part) { CU(cudaFree(c->part)); c->part = nullptr; }
     if (c->tile_ticket) { CU(cudaFree(c->tile_ticket)); c->tile_ticket = nullptr; }
@@ -244,7 +261,9 @@ static int resolve(nbx_ctx *c)
     return NBX_OK;
 }
 
-static void fill_params(const nbx_ctx *c, StepParams &p, int in_buf, float4 *acc_out)
+enum { PHASE_WHOLE = 0, PHASE_LOCAL = 1, PHASE_REMOTE = 2 };
+
+static void fill_params(const nbx_ctx *c, StepParams &p, int in_buf, float4 *acc_out, int phase = PHASE_WHOLE)
 {
     std::memset(&p, 0, sizeof p);
     p.pos_in = c->pos[in_buf];
@@ -265,6 +284,20 @@ static void fill_params(const nbx_ctx *c, StepParams &p, int in_buf, float4 *acc
     p.whole_tiles = c->whole_tiles;
     p.j_splits = c->j_splits;
     p.split_bodies = c->split_bodies;
+    p.j_org = 0;
+    p.j_len = c->n_pad;
+    p.split_base = 0;
+    p.split_total = c->j_splits;
+    const bool overlap = c->world > 1 && c->exchange == NBX_EXCHANGE_NCCL_OVERLAP;
+    if (overlap && phase == PHASE_WHOLE) {           // nbx_accelerations: one launch, s_remote slots
+        p.j_splits = p.split_total = c->s_remote;
+    } else if (phase == PHASE_LOCAL) {
+        p.j_org = c->i_begin; p.j_len = c->i_count;
+        p.j_splits = c->s_local; p.split_base = 0;
+    } else if (phase == PHASE_REMOTE) {
+        p.j_org = (c->i_begin + c->i_count) % c->n_pad; p.j_len = c->n_pad - c->i_count;
+        p.j_splits = c->s_remote; p.split_base = c->s_local;
+    }
     p.dt = c->dt;
     p.eps2 = c->eps2;
     p.world = c->world;
@@ -279,13 +312,13 @@ static void fill_params(const nbx_ctx *c, StepParams &p, int in_buf, float4 *acc
     }
 }
 
-static int launch_step(nbx_ctx *c, int in_buf, float4 *acc_out = nullptr)
+static int launch_step(nbx_ctx *c, int in_buf, float4 *acc_out = nullptr, int phase = PHASE_WHOLE)
 {
     const Variant &v = variants()[c->variant];
     StepParams p;
-    fill_params(c, p, in_buf, acc_out);
+    fill_params(c, p, in_buf, acc_out, phase);
     void *args[] = {&p};
-    const int ctas = c->whole_tiles + (c->i_tiles - c->whole_tiles) * c->j_splits;
+    const int ctas = c->whole_tiles + (c->i_tiles - c->whole_tiles) * p.j_splits;
     CU(cudaLaunchKernel(v.fn, dim3(ctas), dim3(v.threads), args, v.smem, c->stream));
     c->kernel_launches++;
     return NBX_OK;
@@ -322,10 +355,64 @@ static int ensure_ke(nbx_ctx *c, int nsteps)
     return NBX_OK;
 }
 
+// One step's kernel launch(es) on c->stream; flips the ping-pong.
+static int step_compute(nbx_ctx *c)
+{
+    int rc;
+    if (c->world > 1 && c->exchange == NBX_EXCHANGE_NCCL_OVERLAP) {
+        if ((rc = launch_step(c, c->cur, nullptr, PHASE_LOCAL))) return rc;      // needs no remote data
+        if (c->gather_pending) CU(cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
+        if ((rc = launch_step(c, c->cur, nullptr, PHASE_REMOTE))) return rc;     // + combine + epilogue
+    } else {
+        if ((rc = launch_step(c, c->cur))) return rc;
+    }
+    c->cur ^= 1;
+    return NBX_OK;
+}
+
+// The exchange that follows a step (inside ncclGroupStart/End when one thread drives several GPUs).
+static int step_exchange(nbx_ctx *c)
+{
+    if (c->world < 2 || c->exchange == NBX_EXCHANGE_P2P) return NBX_OK;   // P2P: done by the epilogue
+    float4 *buf = c->pos[c->cur];                                          // freshly written shard, in place
+    cudaStream_t st = c->stream;
+    if (c->exchange == NBX_EXCHANGE_NCCL_OVERLAP) {
+        CU(cudaEventRecord(c->ev_step, c->stream));
+        CU(cudaStreamWaitEvent(c->comm_stream, c->ev_step, 0));
+        st = c->comm_stream;
+    }
+    NC(g_nccl.AllGather(buf + c->i_begin, buf, (size_t)c->i_count * 4, ncclFloat, c->comm, st));
+    if (c->exchange == NBX_EXCHANGE_NCCL_OVERLAP) {
+        CU(cudaEventRecord(c->ev_gather, c->comm_stream));
+        c->gather_pending = true;
+    }
+    return NBX_OK;
+}
+
+// Kinetic energies of all shards; leaves c->stream ordered after every outstanding exchange.
+static int finish_run(nbx_ctx *c, int nsteps, bool reduce)
+{
+    if (c->world < 2) return NBX_OK;
+    cudaStream_t st = c->stream;
+    const bool overlap = c->exchange == NBX_EXCHANGE_NCCL_OVERLAP;
+    if (overlap) {
+        CU(cudaEventRecord(c->ev_step, c->stream));
+        CU(cudaStreamWaitEvent(c->comm_stream, c->ev_step, 0));
+        st = c->comm_stream;
+    }
+    if (reduce && nsteps > 0)
+        NC(g_nccl.AllReduce(c->ke_dev, c->ke_dev, (size_t)nsteps, ncclDouble, ncclSum, c->comm, st));
+    if (overlap) {
+        CU(cudaEventRecord(c->ev_gather, c->comm_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
+    }
+    return NBX_OK;
+}
+
 // Enqueue nsteps steps (and their exchanges) on c->stream; no host sync.
 static int enqueue_steps(nbx_ctx *c, int nsteps)
 {
-    const bool nccl_x = c->world > 1 && c->exchange == NBX_EXCHANGE_NCCL;
+    const bool nccl_x = c->world > 1 && c->exchange != NBX_EXCHANGE_P2P;
     int left = nsteps;
     if (c->use_graph && !nccl_x) {
         if (c->cur == 1 && left > 0) {   // graphs start on pos[0]
@@ -348,15 +435,10 @@ static int enqueue_steps(nbx_ctx *c, int nsteps)
         }
     }
     while (left > 0) {
-        int rc = launch_step(c, c->cur);
+        int rc = step_compute(c);
         if (rc) return rc;
-        c->cur ^= 1;
+        if ((rc = step_exchange(c))) return rc;
         --left;
-        if (nccl_x) {
-            // in-place all-gather of the freshly written shard of pos[cur]
-            float4 *buf = c->pos[c->cur];
-            NC(g_nccl.AllGather(buf + c->i_begin, buf, (size_t)c->i_count * 4, ncclFloat, c->comm, c->stream));
-        }
     }
     return NBX_OK;
 }
@@ -424,6 +506,9 @@ int nbx_create(nbx_ctx **out, int n, int device, int rank, int world, float dt, 
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUB(cudaEventCreate(&c->ev0));
     CUB(cudaEventCreate(&c->ev1));
+    CUB(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&c->ev_step, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_gather, cudaEventDisableTiming));
     CUB(cudaMalloc(&c->pos[0], (size_t)c->n_pad * sizeof(float4)));
     CUB(cudaMalloc(&c->pos[1], (size_t)c->n_pad * sizeof(float4)));
     CUB(cudaMalloc(&c->vel, (size_t)c->i_count * sizeof(float4)));
@@ -441,6 +526,7 @@ void nbx_destroy(nbx_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->graph2) cudaGraphExecDestroy(c->graph2);
     if (c->graph16) cudaGraphExecDestroy(c->graph16);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
@@ -450,6 +536,9 @@ void nbx_destroy(nbx_ctx *c)
     cudaFree(c->ke_dev); cudaFree(c->stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_step) cudaEventDestroy(c->ev_step);
+    if (c->ev_gather) cudaEventDestroy(c->ev_gather);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
     delete c;
@@ -465,7 +554,8 @@ int nbx_set_option(nbx_ctx *c, const char *key, long long value)
     } else if (k == "graph") {
         c->opt_graph = value < 0 ? -1 : (value ? 1 : 0);
     } else if (k == "exchange") {
-        if (value != NBX_EXCHANGE_NCCL && value != NBX_EXCHANGE_P2P) return fail(NBX_ERR_ARG, "unknown exchange %lld", value);
+        if (value != NBX_EXCHANGE_NCCL && value != NBX_EXCHANGE_P2P && value != NBX_EXCHANGE_NCCL_OVERLAP)
+            return fail(NBX_ERR_ARG, "unknown exchange %lld", value);
         c->exchange = (int)value;
     } else if (k == "variant") {
         if (value < -1 || value >= (long long)variants().size()) return fail(NBX_ERR_ARG, "variant out of range");
@@ -522,6 +612,7 @@ int nbx_upload(nbx_ctx *c, const float *px, const float *py, const float *pz,
     c->aux_launches++;
     CU(cudaStreamSynchronize(c->stream));
     c->cur = 0;
+    c->gather_pending = false;
     c->uploaded = true;
     return NBX_OK;
 }
@@ -575,8 +666,7 @@ int nbx_run(nbx_ctx *c, int nsteps, double *kenergy_out, double *seconds_out)
     CU(cudaMemsetAsync(c->counters + 1, 0, sizeof(int), c->stream));   // dev_step = 0
     CU(cudaEventRecord(c->ev0, c->stream));
     if ((rc = enqueue_steps(c, nsteps))) return rc;
-    if (c->world > 1 && nsteps > 0)
-        NC(g_nccl.AllReduce(c->ke_dev, c->ke_dev, (size_t)nsteps, ncclDouble, ncclSum, c->comm, c->stream));
+    if ((rc = finish_run(c, nsteps, true))) return rc;
     CU(cudaEventRecord(c->ev1, c->stream));
     if (kenergy_out && nsteps > 0)
         CU(cudaMemcpyAsync(kenergy_out, c->ke_dev, (size_t)nsteps * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -602,7 +692,7 @@ int nbx_run_group(nbx_ctx **ctxs, int count, int nsteps, double *kenergy_out, do
         CU(cudaMemsetAsync(ctxs[g]->counters + 1, 0, sizeof(int), ctxs[g]->stream));
         CU(cudaEventRecord(ctxs[g]->ev0, ctxs[g]->stream));
     }
-    const bool nccl_x = count > 1 && ctxs[0]->exchange == NBX_EXCHANGE_NCCL;
+    const bool nccl_x = count > 1 && ctxs[0]->exchange != NBX_EXCHANGE_P2P;
     if (count == 1) {
         if ((rc = enqueue_steps(ctxs[0], nsteps))) return rc;
     } else {
@@ -610,20 +700,21 @@ int nbx_run_group(nbx_ctx **ctxs, int count, int nsteps, double *kenergy_out, do
         // finished step s, so no GPU may be queued far ahead of the others by this one thread.
         for (int s = 0; s < nsteps; ++s) {
             for (int g = 0; g < count; ++g) {
-                nbx_ctx *c = ctxs[g];
-                CU(cudaSetDevice(c->device));
-                if ((rc = launch_step(c, c->cur))) return rc;
-                c->cur ^= 1;
+                CU(cudaSetDevice(ctxs[g]->device));
+                if ((rc = step_compute(ctxs[g]))) return rc;
             }
             if (nccl_x) {
                 NC(g_nccl.GroupStart());
                 for (int g = 0; g < count; ++g) {
-                    nbx_ctx *c = ctxs[g];
-                    float4 *buf = c->pos[c->cur];
-                    NC(g_nccl.AllGather(buf + c->i_begin, buf, (size_t)c->i_count * 4, ncclFloat, c->comm, c->stream));
+                    CU(cudaSetDevice(ctxs[g]->device));
+                    if ((rc = step_exchange(ctxs[g]))) { g_nccl.GroupEnd(); return rc; }
                 }
                 NC(g_nccl.GroupEnd());
             }
+        }
+        for (int g = 0; g < count; ++g) {            // kinetic energy is summed on the host below
+            CU(cudaSetDevice(ctxs[g]->device));
+            if ((rc = finish_run(ctxs[g], nsteps, false))) return rc;
         }
     }
     std::vector<double> tmp((size_t)std::max(nsteps, 1));

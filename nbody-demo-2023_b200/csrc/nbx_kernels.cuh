@@ -47,8 +47,13 @@ struct StepParams {
     int i_begin, i_count;
     int i_tiles;            // CTAs' worth of i-bodies in this shard
     int whole_tiles;        // tiles [0, whole_tiles) are not split along j
-    int j_splits;           // split count of tiles [whole_tiles, i_tiles)
+    int j_splits;           // split count of tiles [whole_tiles, i_tiles) in THIS launch
     int split_bodies;       // i-bodies covered by split tiles (stride of `part`)
+    // A launch may cover only a window of the j-bodies (NCCL-overlap mode runs a step as two
+    // launches: the rank's own j-shard while the all-gather is in flight, then the rest):
+    int j_org, j_len;       // j window = [j_org, j_org + j_len) modulo n_pad (multiples of 8)
+    int split_base;         // partial slot of this launch's split 0
+    int split_total;        // contributors per split tile over all launches of the step
     float dt, eps2;
     // P2P exchange (world > 1 and exchange == P2P): peers' replicas and completion flags
     int world, rank, p2p;
@@ -151,16 +156,18 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     int *s_flag = reinterpret_cast<int *>(red + WARPS);
 
     const int tid = threadIdx.x;
-    int tile = blockIdx.x, split = 0, nsplit = 1;
+    int tile = blockIdx.x, split = 0, nsplit = 1, contributors = 1;
     if (tile >= p.whole_tiles) {
         const int r = tile - p.whole_tiles;
         tile = p.whole_tiles + r / p.j_splits;
         split = r % p.j_splits;
         nsplit = p.j_splits;
+        contributors = p.split_total;
     }
 
-    // ---- j range of this CTA, in 8-body chunks so every TMA copy is 128-byte granular
-    const int chunks = p.n_pad >> 3;
+    // ---- j range of this CTA inside the launch's window, in 8-body chunks so every TMA copy
+    //      is 128-byte granular
+    const int chunks = p.j_len >> 3;
     const int jb = (int)(((long long)chunks * split) / nsplit) << 3;
     const int je = (int)(((long long)chunks * (split + 1)) / nsplit) << 3;
     const int ntiles = (je - jb + TJ - 1) / TJ;
@@ -185,11 +192,14 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     __syncthreads();
 
     auto issue_tile = [&](int t) {
-        const int j0 = jb + t * TJ;
-        const int cnt = min(TJ, je - j0);
+        const int cnt = min(TJ, je - (jb + t * TJ));
+        int j0 = p.j_org + jb + t * TJ;                    // window may wrap around n_pad
+        if (j0 >= p.n_pad) j0 -= p.n_pad;
+        const int head = min(cnt, p.n_pad - j0);
         const int st = t % STAGES;
         mbar_expect_tx(&full[st], (uint32_t)cnt * 16u);
-        tma_load_1d(tiles + st * TJ, p.pos_in + j0, (uint32_t)cnt * 16u, &full[st]);
+        tma_load_1d(tiles + st * TJ, p.pos_in + j0, (uint32_t)head * 16u, &full[st]);
+        if (head < cnt) tma_load_1d(tiles + st * TJ + head, p.pos_in, (uint32_t)(cnt - head) * 16u, &full[st]);
     };
     if (tid == 0) {
 #pragma unroll
@@ -279,10 +289,10 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     }
 
     // ---- j-split: park partials, the last CTA of this i-tile adds them in split order
-    if (nsplit > 1) {
+    if (contributors > 1) {
         constexpr int BI = THREADS * R;
         const int tb0 = p.whole_tiles * BI;                    // first body held in `part`
-        float4 *mine = p.part + (size_t)split * p.split_bodies - tb0;
+        float4 *mine = p.part + (size_t)(p.split_base + split) * p.split_bodies - tb0;
 #pragma unroll
         for (int k = 0; k < R2; ++k) {
             const int ip = pair_base + k * THREADS;
@@ -294,7 +304,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         __threadfence();
         __syncthreads();
         int *ticket = &p.tile_ticket[tile - p.whole_tiles];
-        if (tid == 0) *s_flag = (atomicAdd(ticket, 1) == nsplit - 1);
+        if (tid == 0) *s_flag = (atomicAdd(ticket, 1) == contributors - 1);
         __syncthreads();
         if (!*s_flag) return;
         __threadfence();
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                 for (int h = 0; h < 2; ++h) {
                     float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll 8                                       // batch the L2 loads; the adds stay in split order
-                    for (int s = 0; s < nsplit; ++s) {
+                    for (int s = 0; s < contributors; ++s) {
                         const float4 v = __ldcg(&p.part[(size_t)s * p.split_bodies + (2 * ip + h - tb0)]);
                         sx += v.x; sy += v.y; sz += v.z;
                     }

@@ -8,7 +8,7 @@
 //
 // Environment (all optional; none changes `./nbody.x N S` output):
 //   NBODY_GPUS=G        shard the i-bodies over G GPUs of this node (default 1)
-//   NBODY_EXCHANGE=nccl|p2p   multi-GPU position exchange (default nccl)
+//   NBODY_EXCHANGE=nccl|nccl_overlap|p2p   multi-GPU position exchange (default nccl)
 //   NBODY_SFREQ=k       print a row every k steps (default 50, ver0:31)
 //   NBODY_IC=uniform|plummer  initial positions (default: the reference's uniform cube)
 //   NBODY_DUMP=file     write the final state (NBXD format, see oracle/ref_harness.cpp)
@@ -121,7 +121,8 @@ void GSimulation::start()
     const float Gconst = 6.67259e-11f;      // ver2/GSimulation.cpp:116
     std::vector<nbx_ctx *> ctx((size_t)G, nullptr);
     const char *xch = std::getenv("NBODY_EXCHANGE");
-    const long long exchange = (xch && std::strcmp(xch, "p2p") == 0) ? NBX_EXCHANGE_P2P : NBX_EXCHANGE_NCCL;
+    const long long exchange = (xch && std::strcmp(xch, "p2p") == 0) ? NBX_EXCHANGE_P2P
+                               : (xch && std::strcmp(xch, "nccl_overlap") == 0) ? NBX_EXCHANGE_NCCL_OVERLAP : NBX_EXCHANGE_NCCL;
     for (int g = 0; g < G; ++g) {
         if (nbx_create(&ctx[g], n, g, g, G, get_tstep(), Gconst, softeningSquared)) die("nbx_create");
         if (forced_variant >= 0 && nbx_set_option(ctx[g], "variant", forced_variant)) die("variant");

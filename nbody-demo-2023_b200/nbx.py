@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libnbx.so")
 
 EXCHANGE_NCCL = 0
 EXCHANGE_P2P = 1
+EXCHANGE_NCCL_OVERLAP = 2
 UNIQUE_ID_BYTES = 128
 P2P_BLOB_BYTES = 256
 
