@@ -305,6 +305,8 @@ def main():
                      "frac": round(achieved_tflops / peak_tflops, 4), "traffic": traffic,
                      "peak_source": f"{sm_count} SMs x 128 FP32 lanes x 2 x sm_max_mhz {peaks['sm_max_mhz']} ({peak_kind} MEASURED_PEAKS.json) x {args.gpus} GPU",
                      "flop_per_pair": FLOP_PER_PAIR,
+                     "hbm": {"algorithmic_bytes_per_launch": 64 * n // args.gpus, "achieved_gbs": round(64.0 * n / args.gpus / (kernel_s / args.steps) / 1e9, 2),
+                             "peak_gbs": peaks.get("hbm_gbs"), "frac": round(64.0 * n / args.gpus / (kernel_s / args.steps) / 1e9 / peaks.get("hbm_gbs", 6650.0), 6)},
                      "note": "compute-bound on the FP32 pipe, not HBM or tensor: 12 FP32 lane-ops per pair, 6 of them FMAs, so 20 algorithmic flop/pair caps at 20/24 = 83.3% of the FMA peak; HBM need is 64 B/body/step"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
     }
