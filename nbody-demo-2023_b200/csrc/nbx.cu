@@ -130,6 +130,7 @@ static const std::vector<Variant> &variants()
         make_variant<2, 512, 512, 4, 2, 1>("r4_t512_u2"),
         make_variant<2, 64, 128, 4, 2, 8>("r4_t64_u2"),
         make_variant<2, 256, 256, 4, 2, 2, 1>("r4_t256_u2_sacc"),
+        make_variant<2, 256, 256, 4, 2, 2, 15>("r4_t256_u2_scalar"),
     };
     return v;
 }

@@ -124,6 +124,23 @@ __device__ __forceinline__ void st_release_sys(int *p, int v)
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Packed (FADD2/FMUL2/FFMA2) or scalar form of a two-lane FP32 op.
+template <bool SCALAR> __device__ __forceinline__ float2 add2(float2 a, float2 b)
+{
+    if (SCALAR) return make_float2(a.x + b.x, a.y + b.y);
+    return __fadd2_rn(a, b);
+}
+template <bool SCALAR> __device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+    if (SCALAR) return make_float2(a.x * b.x, a.y * b.y);
+    return __fmul2_rn(a, b);
+}
+template <bool SCALAR> __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
+{
+    if (SCALAR) return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+    return __ffma2_rn(a, b, c);
+}
+
 // Shared-memory footprint of one CTA (host uses the same formula).
 template <int THREADS, int TJ, int STAGES>
 constexpr int step_smem_bytes()
@@ -249,29 +266,24 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                 const float2 zj = make_float2(q1.x, q1.y), mj = make_float2(q1.z, q1.w);
 #pragma unroll
                 for (int b = 0; b < R; ++b) {
-                    const float2 dx = __fadd2_rn(xj, nx[b]);
-                    const float2 dy = __fadd2_rn(yj, ny[b]);
-                    const float2 dz = __fadd2_rn(zj, nz[b]);
-                    float2 r2 = __ffma2_rn(dx, dx, eps2v);
-                    r2 = __ffma2_rn(dy, dy, r2);
-                    r2 = __ffma2_rn(dz, dz, r2);
+                    // MATH bit set = that op group is issued as scalar instead of packed instructions
+                    // (8: subtract, 4: r^2 chain, 2: Gm*inv^3, 1: accumulate).  0 = all packed is
+                    // the default and the fastest of the 16 mixes: 71.1% of FP32 peak against 62.5%
+                    // all-scalar, every scalarised group costs 2.6-4.6%
+                    // (profiles/r01_ab_packed_vs_scalar_n262144.log).
+                    const float2 dx = add2<(MATH & 8) != 0>(xj, nx[b]);
+                    const float2 dy = add2<(MATH & 8) != 0>(yj, ny[b]);
+                    const float2 dz = add2<(MATH & 8) != 0>(zj, nz[b]);
+                    float2 r2 = fma2<(MATH & 4) != 0>(dx, dx, eps2v);
+                    r2 = fma2<(MATH & 4) != 0>(dy, dy, r2);
+                    r2 = fma2<(MATH & 4) != 0>(dz, dz, r2);
                     const float2 inv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
-                    const float2 inv2 = __fmul2_rn(inv, inv);
-                    const float2 mi = __fmul2_rn(mj, inv);
-                    const float2 s = __fmul2_rn(inv2, mi);
-                    if (MATH == 0) {
-                        ax[b] = __ffma2_rn(dx, s, ax[b]);
-                        ay[b] = __ffma2_rn(dy, s, ay[b]);
-                        az[b] = __ffma2_rn(dz, s, az[b]);
-                    } else {
-                        // MATH 1 (kept for the record, not the default): a packed FMA with three
-                        // distinct 64-bit register operands issues at half rate in isolation
-                        // (tools/ubench2.cu), the scalar form does not -- yet in this loop the
-                        // all-packed form above is 2% faster (profiles/r01_sweep_n262144.log).
-                        ax[b].x = fmaf(dx.x, s.x, ax[b].x); ax[b].y = fmaf(dx.y, s.y, ax[b].y);
-                        ay[b].x = fmaf(dy.x, s.x, ay[b].x); ay[b].y = fmaf(dy.y, s.y, ay[b].y);
-                        az[b].x = fmaf(dz.x, s.x, az[b].x); az[b].y = fmaf(dz.y, s.y, az[b].y);
-                    }
+                    const float2 inv2 = mul2<(MATH & 2) != 0>(inv, inv);
+                    const float2 mi = mul2<(MATH & 2) != 0>(mj, inv);
+                    const float2 s = mul2<(MATH & 2) != 0>(inv2, mi);
+                    ax[b] = fma2<(MATH & 1) != 0>(dx, s, ax[b]);
+                    ay[b] = fma2<(MATH & 1) != 0>(dy, s, ay[b]);
+                    az[b] = fma2<(MATH & 1) != 0>(dz, s, az[b]);
                 }
             }
         }

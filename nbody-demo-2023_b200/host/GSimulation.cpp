@@ -12,6 +12,7 @@
 //   NBODY_SFREQ=k       print a row every k steps (default 50, ver0:31)
 //   NBODY_IC=uniform|plummer  initial positions (default: the reference's uniform cube)
 //   NBODY_DUMP=file     write the final state (NBXD format, see oracle/ref_harness.cpp)
+//   NBODY_RESTORE=file  start from a state written by NBODY_DUMP instead of the initial conditions
 //   NBODY_VARIANT=i, NBODY_JSPLITS=s, NBODY_GRAPH=0|1   kernel-shape knobs
 #include "GSimulation.hpp"
 
@@ -99,6 +100,21 @@ void GSimulation::start()
     init_vel();
     init_acc();
     init_mass();
+    if (const char *rs = std::getenv("NBODY_RESTORE")) {   // the reference has no on-disk format; this is ours
+        FILE *f = std::fopen(rs, "rb");
+        char magic[4];
+        int32_t hdr[2];
+        float kef;
+        double secs;
+        bool ok = f && std::fread(magic, 1, 4, f) == 4 && std::memcmp(magic, "NBXD", 4) == 0 &&
+                  std::fread(hdr, sizeof(int32_t), 2, f) == 2 && hdr[0] == n &&
+                  std::fread(&kef, sizeof(float), 1, f) == 1 && std::fread(&secs, sizeof(double), 1, f) == 1;
+        ParticleSoA &p = *particles;
+        for (auto *v : {&p.pos_x, &p.pos_y, &p.pos_z, &p.vel_x, &p.vel_y, &p.vel_z, &p.mass})
+            ok = ok && std::fread(v->data(), sizeof(float), (size_t)n, f) == (size_t)n;
+        if (f) std::fclose(f);
+        if (!ok) { std::cerr << "nbody.x: NBODY_RESTORE: cannot read a " << n << "-body NBXD state from " << rs << std::endl; std::exit(1); }
+    }
 
     // ---- ver5_all knobs: a CPU share cannot be honoured (no CPU path here, by design)
     if (_devices == 1 || _devices == 3) {

@@ -318,3 +318,21 @@ def test_ver5_all_style_cli(pkg, golden):
         assert abs(float(x[2]) - float(row["kenergy"])) / float(row["kenergy"]) < 2e-4
     r = subprocess.run([pkg.CLI_ALL_PATH, "2000", "100", "cpu+gpu"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "GPU-only" in r.stderr
+
+
+def test_cli_dump_restore_continues_bitwise(pkg, oracle, tmp_path):
+    """10 steps == 4 steps, dump, restore, 6 steps (state files carry everything the path needs)."""
+    d10, d4, d46 = (str(tmp_path / x) for x in ("a.bin", "b.bin", "c.bin"))
+    base = dict(os.environ, NBODY_SFREQ="2")
+    for args, env in ((["3000", "10"], dict(base, NBODY_DUMP=d10)),
+                      (["3000", "4"], dict(base, NBODY_DUMP=d4)),
+                      (["3000", "6"], dict(base, NBODY_RESTORE=d4, NBODY_DUMP=d46))):
+        r = subprocess.run([pkg.CLI_PATH] + args, capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr
+    a, ke_a, _, _ = oracle.read_dump(d10)
+    c, ke_c, _, _ = oracle.read_dump(d46)
+    assert ke_a == ke_c
+    for f in oracle.State.FIELDS:
+        assert np.array_equal(getattr(a, f), getattr(c, f)), f
+    r = subprocess.run([pkg.CLI_PATH, "2999", "2"], capture_output=True, text=True, env=dict(base, NBODY_RESTORE=d4), timeout=60)
+    assert r.returncode == 1 and "NBODY_RESTORE" in r.stderr
