@@ -164,7 +164,7 @@ struct nbx_ctx {
     bool uploaded = false;
 
     // configuration
-    int variant = 0, opt_variant = -1, opt_splits = 0, opt_graph = -1, exchange = NBX_EXCHANGE_NCCL;
+    int variant = 0, opt_variant = -1, opt_splits = 0, opt_graph = -1, opt_pdl = -1, exchange = NBX_EXCHANGE_NCCL;
     bool resolved = false;
     int i_tiles = 0, whole_tiles = 0, j_splits = 1, split_bodies = 0, ctas_per_sm = 0, use_graph = 0;
 
@@ -320,7 +320,21 @@ static int launch_step(nbx_ctx *c, int in_buf, float4 *acc_out = nullptr, int ph
     fill_params(c, p, in_buf, acc_out, phase);
     void *args[] = {&p};
     const int ctas = c->whole_tiles + (c->i_tiles - c->whole_tiles) * p.j_splits;
-    CU(cudaLaunchKernel(v.fn, dim3(ctas), dim3(v.threads), args, v.smem, c->stream));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(v.threads);
+    cfg.dynamicSmemBytes = v.smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap our prologue with
+    attr[0].val.programmaticStreamSerializationAllowed = 1;            // the previous step's tail
+    cfg.attrs = attr;
+    // Auto: only for grids of many waves.  With a single under-subscribed wave (N = 16 384: 144 CTAs)
+    // the early-scheduled dependents take the free slots unevenly and the next step runs two CTAs
+    // on some SMs and none on others: measured 0.19 ms instead of 0.114 ms per step.
+    const bool pdl = c->opt_pdl >= 0 ? c->opt_pdl != 0 : ctas >= 4 * c->sm_count;
+    cfg.numAttrs = pdl ? 1 : 0;
+    CU(cudaLaunchKernelExC(&cfg, v.fn, args));
     c->kernel_launches++;
     return NBX_OK;
 }
@@ -554,6 +568,8 @@ int nbx_set_option(nbx_ctx *c, const char *key, long long value)
         c->opt_splits = (int)value;
     } else if (k == "graph") {
         c->opt_graph = value < 0 ? -1 : (value ? 1 : 0);
+    } else if (k == "pdl") {
+        c->opt_pdl = value < 0 ? -1 : (value ? 1 : 0);
     } else if (k == "exchange") {
         if (value != NBX_EXCHANGE_NCCL && value != NBX_EXCHANGE_P2P && value != NBX_EXCHANGE_NCCL_OVERLAP)
             return fail(NBX_ERR_ARG, "unknown exchange %lld", value);

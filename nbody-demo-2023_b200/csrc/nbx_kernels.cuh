@@ -189,12 +189,19 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     const int je = (int)(((long long)chunks * (split + 1)) / nsplit) << 3;
     const int ntiles = (je - jb + TJ - 1) / TJ;
 
+    // Programmatic dependent launch: let the next step's grid be scheduled as soon as SM resources
+    // free up, and do our own set-up (barrier init) before waiting for the previous step's grid --
+    // only what follows griddepcontrol.wait may read what that grid wrote.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], WARPS);
         }
         mbar_fence_init();
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid == 0) {
         // P2P exchange: every rank must have finished the previous step (its epilogue wrote
         // into OUR pos_in) before we read it.  Peers run on other GPUs; no kernel on this
         // GPU is waited on.
