@@ -10,7 +10,7 @@ n, steps, reps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 names = sys.argv[4].split(",")
 splits = [int(x) for x in sys.argv[5].split(",")]
 graph = int(sys.argv[6]) if len(sys.argv) > 6 else 0
-pdls = [int(x) for x in sys.argv[7].split(",")] if len(sys.argv) > 7 else [1]
+pdls = [int(x) for x in sys.argv[7].split(",")] if len(sys.argv) > 7 else [-1]
 allv = nbx.variant_names()
 arrs = nbx.ic(n)
 ctxs = {}
@@ -20,7 +20,7 @@ for nm in names:
         c = nbx.Context(n)
         c.set_option("variant", allv.index(nm)); c.set_option("j_splits", sp); c.set_option("graph", graph); c.set_option("pdl", pdl)
         c.upload(*arrs); c.run(max(2, steps // 4))
-        ctxs[(nm + ("" if pdl else "_nopdl"), sp)] = c
+        ctxs[(nm + {-1: "", 0: "_nopdl", 1: "_pdl"}[pdl], sp)] = c
 res = {k: [] for k in ctxs}
 for r in range(reps):
     for k, c in ctxs.items():
