@@ -234,7 +234,13 @@ static int resolve(nbx_ctx *c)
         c->s_remote = splits > 0 ? splits : pick_splits(c->i_tiles, c->n_pad - c->i_count, c->sm_count);
         splits = c->s_local + c->s_remote;
     } else if (splits <= 0) {
-        c->whole_tiles = (c->i_tiles / c->sm_count) * c->sm_count;
+        // Unsplit tiles only when they fill >= 3 whole rounds of the SMs.  The first wave is not
+        // dealt evenly (traced at 152 tiles: 6 of 148 SMs received two whole-tile CTAs, 6 none) and
+        // co-resident CTAs do not share an SM fairly (the older one runs, the newer one starves),
+        // so with 1-2 rounds of long CTAs the step took 2x; from 3 rounds on the short tail CTAs
+        // even it out (profiles/r01_hybrid_probe.log).
+        const int rounds = c->i_tiles / c->sm_count;
+        c->whole_tiles = rounds >= 3 ? rounds * c->sm_count : 0;
         const int tail = c->i_tiles - c->whole_tiles;
         splits = tail > 0 ? pick_splits(tail, c->n_pad, c->sm_count) : 1;
     }

@@ -20,8 +20,10 @@
 //     last CTA sums in tile order) and, on several GPUs, the NVLink stores of the
 //     updated records into every peer's replica all run in the same kernel's epilogue;
 //   * a j-split with a last-arriver combine in fixed split order fills the 148 SMs: the first
-//     `whole_tiles` i-tiles (whole rounds of the SM count) run unsplit, the remaining tail tiles
-//     -- all tiles when there are fewer than SMs -- are cut `j_splits` ways along j.
+//     `whole_tiles` i-tiles (whole rounds of the SM count, when there are at least three) run
+//     unsplit, the remaining tail tiles are cut `j_splits` ways along j.  (A persistent stream-K
+//     grid -- equal spans of the tile-major (i-tile, j-chunk) work, one CTA per SM -- measured
+//     within +-1% of this at N = 2000 ... 131 072 and was dropped.)
 #pragma once
 
 #include <cuda_runtime.h>
@@ -149,34 +151,78 @@ constexpr int step_smem_bytes()
 }
 
 // ------------------------------------------------------------------------------
-//  One segment of work: the forces of i-tile `tile` from the j-bodies [jb, je) of the launch's
-//  window, then either the fused epilogue (contributors == 1) or park-partials / last-arriver
-//  combine + epilogue.  `ring` counts the TMA tiles the CTA has pushed through its shared-memory
-//  ring so far, so a CTA could run several segments back to back.  (A persistent stream-K grid
-//  built on that -- equal spans of the tile-major (i-tile, j-chunk) work, one CTA per SM -- was
-//  measured within +-1% of the split grid at N = 2000 ... 131 072 and was dropped.)
-//  A `return` in here ends the segment, not the kernel; every exit is CTA-uniform.
+//  The step kernel.
+//    R2      i-body PAIRS register-blocked per thread (R = 2*R2 bodies)
+//    THREADS CTA size;  BI = THREADS*R i-bodies per CTA
+//    TJ      j-bodies per TMA stage (multiple of 8)
+//    STAGES  ring depth (>= 3: one being read, one landed, one in flight)
+//    UNROLL  j-records per inner-loop trip (1, 2 or 4)
+//    MINB    __launch_bounds__ min CTAs per SM
+//  grid = whole_tiles + (i_tiles - whole_tiles) * j_splits CTAs, whole tiles first
 // ------------------------------------------------------------------------------
-template <int R2, int THREADS, int TJ, int STAGES, int UNROLL, int MATH>
-__device__ __forceinline__ void run_segment(const StepParams &p, float4 *tiles, uint64_t *full, uint64_t *empty,
-                                            double *red, int *s_flag, const int tile, const int jb, const int je,
-                                            const int slot, const int contributors, const int ticket_idx,
-                                            const int tb0, const int part_stride, int &ring)
+template <int R2, int THREADS, int TJ, int STAGES, int UNROLL, int MINB, int MATH = 0>
+__global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_constant__ StepParams p)
 {
     constexpr int R = 2 * R2;
     constexpr int WARPS = THREADS / 32;
+    static_assert(TJ % 8 == 0 && STAGES >= 3 && (UNROLL == 1 || UNROLL == 2 || UNROLL == 4), "shape");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + STAGES * TJ * 16);
+    uint64_t *empty = full + STAGES;
+    double *red = reinterpret_cast<double *>(empty + STAGES);
+    int *s_flag = reinterpret_cast<int *>(red + WARPS);
+
     const int tid = threadIdx.x;
+    int tile = blockIdx.x, split = 0, nsplit = 1, contributors = 1;
+    if (tile >= p.whole_tiles) {
+        const int r = tile - p.whole_tiles;
+        tile = p.whole_tiles + r / p.j_splits;
+        split = r % p.j_splits;
+        nsplit = p.j_splits;
+        contributors = p.split_total;
+    }
+
+    // ---- j range of this CTA inside the launch's window, in 8-body chunks so every TMA copy
+    //      is 128-byte granular
+    const int chunks = p.j_len >> 3;
+    const int jb = (int)(((long long)chunks * split) / nsplit) << 3;
+    const int je = (int)(((long long)chunks * (split + 1)) / nsplit) << 3;
     const int ntiles = (je - jb + TJ - 1) / TJ;
-    const int ring0 = ring;           // tiles this CTA has already pushed through the ring
-    ring += ntiles;
+
+    // Programmatic dependent launch: let the next step's grid be scheduled as soon as SM resources
+    // free up, and do our own set-up (barrier init) before waiting for the previous step's grid --
+    // only what follows griddepcontrol.wait may read what that grid wrote.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], WARPS);
+        }
+        mbar_fence_init();
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid == 0) {
+        // P2P exchange: every rank must have finished the previous step (its epilogue wrote
+        // into OUR pos_in) before we read it.  Peers run on other GPUs; no kernel on this
+        // GPU is waited on.
+        if (p.p2p) {
+            const int epoch = *p.dev_epoch;
+            for (int g = 0; g < p.world; ++g)
+                if (g != p.rank)
+                    while (ld_acquire_sys(&p.my_flags[g]) < epoch) { }
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+    }
+    __syncthreads();
+
     auto issue_tile = [&](int t) {
         const int cnt = min(TJ, je - (jb + t * TJ));
         int j0 = p.j_org + jb + t * TJ;                    // window may wrap around n_pad
         if (j0 >= p.n_pad) j0 -= p.n_pad;
         const int head = min(cnt, p.n_pad - j0);
-        const int u = ring0 + t;
-        const int st = u % STAGES;
-        if (u >= STAGES) mbar_wait(&empty[st], ((u / STAGES) - 1) & 1);   // every warp is done with its last tenant
+        const int st = t % STAGES;
         mbar_expect_tx(&full[st], (uint32_t)cnt * 16u);
         tma_load_1d(tiles + st * TJ, p.pos_in + j0, (uint32_t)head * 16u, &full[st]);
         if (head < cnt) tma_load_1d(tiles + st * TJ + head, p.pos_in, (uint32_t)(cnt - head) * 16u, &full[st]);
@@ -208,9 +254,15 @@ __device__ __forceinline__ void run_segment(const StepParams &p, float4 *tiles, 
 
     // ---- sweep the j tiles
     for (int t = 0; t < ntiles; ++t) {
-        if (tid == 0 && t + STAGES - 2 < ntiles) issue_tile(t + STAGES - 2);   // refill two tiles behind the reader
-        const int st = (ring0 + t) % STAGES;
-        mbar_wait(&full[st], ((ring0 + t) / STAGES) & 1);
+        if (tid == 0) {
+            const int u = t + STAGES - 2;                  // refill two tiles behind the reader
+            if (u < ntiles) {
+                if (u >= STAGES) mbar_wait(&empty[u % STAGES], ((u / STAGES) - 1) & 1);
+                issue_tile(u);
+            }
+        }
+        const int st = t % STAGES;
+        mbar_wait(&full[st], (t / STAGES) & 1);
         const float4 *rec = tiles + st * TJ;
         const int nrec = min(TJ, je - (jb + t * TJ)) >> 1;  // records in this tile (multiple of 4)
 #pragma unroll 1
@@ -259,7 +311,9 @@ __device__ __forceinline__ void run_segment(const StepParams &p, float4 *tiles, 
 
     // ---- j-split: park partials, the last CTA of this i-tile adds them in split order
     if (contributors > 1) {
-        float4 *mine = p.part + (size_t)slot * part_stride - tb0;
+        constexpr int BI = THREADS * R;
+        const int tb0 = p.whole_tiles * BI;                    // first body held in `part`
+        float4 *mine = p.part + (size_t)(p.split_base + split) * p.split_bodies - tb0;
 #pragma unroll
         for (int k = 0; k < R2; ++k) {
             const int ip = pair_base + k * THREADS;
@@ -270,7 +324,7 @@ __device__ __forceinline__ void run_segment(const StepParams &p, float4 *tiles, 
         }
         __threadfence();
         __syncthreads();
-        int *ticket = &p.tile_ticket[ticket_idx];
+        int *ticket = &p.tile_ticket[tile - p.whole_tiles];
         if (tid == 0) *s_flag = (atomicAdd(ticket, 1) == contributors - 1);
         __syncthreads();
         if (!*s_flag) return;
@@ -285,7 +339,7 @@ __device__ __forceinline__ void run_segment(const StepParams &p, float4 *tiles, 
                     float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll 8                                       // batch the L2 loads; the adds stay in split order
                     for (int s = 0; s < contributors; ++s) {
-                        const float4 v = __ldcg(&p.part[(size_t)s * part_stride + (2 * ip + h - tb0)]);
+                        const float4 v = __ldcg(&p.part[(size_t)s * p.split_bodies + (2 * ip + h - tb0)]);
                         sx += v.x; sy += v.y; sz += v.z;
                     }
                     fx[2 * k + h] = sx; fy[2 * k + h] = sy; fz[2 * k + h] = sz;
@@ -367,83 +421,6 @@ __device__ __forceinline__ void run_segment(const StepParams &p, float4 *tiles, 
                 if (g != p.rank) st_release_sys(&p.peer_flags[g][p.rank], epoch);
         }
     }
-}
-
-// Common CTA set-up: mbarrier ring, programmatic-dependent-launch handshake, P2P epoch wait.
-template <int THREADS, int STAGES>
-__device__ __forceinline__ void cta_prologue(const StepParams &p, uint64_t *full, uint64_t *empty)
-{
-    constexpr int WARPS = THREADS / 32;
-    const int tid = threadIdx.x;
-    // Programmatic dependent launch: let the next step's grid be scheduled as soon as SM resources
-    // free up, and do our own set-up (barrier init) before waiting for the previous step's grid --
-    // only what follows griddepcontrol.wait may read what that grid wrote.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], WARPS);
-        }
-        mbar_fence_init();
-    }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (tid == 0) {
-        // P2P exchange: every rank must have finished the previous step (its epilogue wrote
-        // into OUR pos_in) before we read it.  Peers run on other GPUs; no kernel on this
-        // GPU is waited on.
-        if (p.p2p) {
-            const int epoch = *p.dev_epoch;
-            for (int g = 0; g < p.world; ++g)
-                if (g != p.rank)
-                    while (ld_acquire_sys(&p.my_flags[g]) < epoch) { }
-            asm volatile("fence.proxy.async;" ::: "memory");
-        }
-    }
-    __syncthreads();
-}
-
-// ------------------------------------------------------------------------------
-//  The step kernel.
-//    R2      i-body PAIRS register-blocked per thread (R = 2*R2 bodies)
-//    THREADS CTA size;  BI = THREADS*R i-bodies per CTA
-//    TJ      j-bodies per TMA stage (multiple of 8)
-//    STAGES  ring depth (>= 3: one being read, one landed, one in flight)
-//    UNROLL  j-records per inner-loop trip (1, 2 or 4)
-//    MINB    __launch_bounds__ min CTAs per SM
-//  grid = whole_tiles + (i_tiles - whole_tiles) * j_splits CTAs, whole tiles first
-// ------------------------------------------------------------------------------
-template <int R2, int THREADS, int TJ, int STAGES, int UNROLL, int MINB, int MATH = 0>
-__global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_constant__ StepParams p)
-{
-    constexpr int WARPS = THREADS / 32;
-    static_assert(TJ % 8 == 0 && STAGES >= 3 && (UNROLL == 1 || UNROLL == 2 || UNROLL == 4), "shape");
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + STAGES * TJ * 16);
-    uint64_t *empty = full + STAGES;
-    double *red = reinterpret_cast<double *>(empty + STAGES);
-    int *s_flag = reinterpret_cast<int *>(red + WARPS);
-
-    int tile = blockIdx.x, split = 0, nsplit = 1, contributors = 1;
-    if (tile >= p.whole_tiles) {
-        const int r = tile - p.whole_tiles;
-        tile = p.whole_tiles + r / p.j_splits;
-        split = r % p.j_splits;
-        nsplit = p.j_splits;
-        contributors = p.split_total;
-    }
-    // ---- j range of this CTA inside the launch's window, in 8-body chunks so every TMA copy
-    //      is 128-byte granular
-    const int chunks = p.j_len >> 3;
-    const int jb = (int)(((long long)chunks * split) / nsplit) << 3;
-    const int je = (int)(((long long)chunks * (split + 1)) / nsplit) << 3;
-
-    cta_prologue<THREADS, STAGES>(p, full, empty);
-    int ring = 0;
-    run_segment<R2, THREADS, TJ, STAGES, UNROLL, MATH>(p, tiles, full, empty, red, s_flag, tile, jb, je,
-                                                      p.split_base + split, contributors, tile - p.whole_tiles,
-                                                      p.whole_tiles * (THREADS * 2 * R2), p.split_bodies, ring);
 }
 
 // ------------------------------------------------------------------------------

@@ -48,6 +48,8 @@ def lib() -> C.CDLL:
             fn.restype = C.c_int
         L.oracle_acc_fp64.argtypes = [C.c_int] + [_f32p] * 4 + [C.c_int, _i32p] + [_f64p] * 3
         L.oracle_acc_fp64.restype = None
+        L.oracle_acc_f32.argtypes = [C.c_int] + [_f32p] * 4 + [C.c_int, _i32p] + [_f32p] * 3
+        L.oracle_acc_f32.restype = None
         L.oracle_kenergy_fp64.argtypes = [C.c_int] + [_f32p] * 4
         L.oracle_kenergy_fp64.restype = C.c_double
         L.oracle_gflop_per_step.argtypes = [C.c_int]
@@ -103,6 +105,14 @@ def acc_fp64(state: State, sel: np.ndarray) -> np.ndarray:
     sel = np.ascontiguousarray(sel, dtype=np.int32)
     out = [np.zeros(sel.size, dtype=np.float64) for _ in range(3)]
     lib().oracle_acc_fp64(state.n, state.px, state.py, state.pz, state.mass, sel.size, sel, *out)
+    return np.stack(out, axis=1)
+
+
+def acc_f32(state: State, sel: np.ndarray) -> np.ndarray:
+    """Reference-order float accelerations of the selected bodies (what ver2 holds in acc[])."""
+    sel = np.ascontiguousarray(sel, dtype=np.int32)
+    out = [np.zeros(sel.size, dtype=np.float32) for _ in range(3)]
+    lib().oracle_acc_f32(state.n, state.px, state.py, state.pz, state.mass, sel.size, sel, *out)
     return np.stack(out, axis=1)
 
 

@@ -87,6 +87,19 @@ def test_fp64_truth_agrees_with_float_oracle(oracle):
     assert abs(ke - ke32) / ke < 1e-5
 
 
+def test_float_sampled_accelerations_match_serial_oracle(oracle):
+    # oracle_acc_f32 is the force half of oracle_run_ver2: v' - v == a*dt exactly when v == 0
+    s = oracle.ic_uniform(3000)
+    s.vx[:] = 0; s.vy[:] = 0; s.vz[:] = 0
+    sel = np.arange(0, 3000, 7, dtype=np.int32)
+    a = oracle.acc_f32(s, sel)
+    s1 = s.copy()
+    oracle.run(s1, 1, variant="ver2")
+    dt = np.float32(0.1)
+    assert np.array_equal(s1.vx[sel], a[:, 0] * dt)                       # vel.x: unfused mul
+    assert np.array_equal(s1.vy[sel], np.float32(0) + a[:, 1] * dt)       # fma(a, dt, 0) == a*dt
+
+
 def test_flop_convention(oracle):
     # ver0/GSimulation.cpp:122
     assert oracle.gflop_per_step(2000) == pytest.approx(1e-9 * (29 * 2000.0 ** 2 + 19 * 2000.0))
