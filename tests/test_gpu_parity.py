@@ -283,8 +283,8 @@ def test_hybrid_whole_plus_split_tail(nbx, oracle):
     assert 0 < info["whole_tiles"] < info["i_tiles"] and info["j_splits"] > 1
     ke1, out1, info1 = gpu_run(nbx, arrs, 2, j_splits=1)
     assert info1["whole_tiles"] == info1["i_tiles"]
-    assert np.max(np.abs(ke - ke1) / ke1) < 1e-6
-    assert rel_l2(np.stack(out[:3], axis=1), np.stack(out1[:3], axis=1)) < 1e-6
+    assert np.max(np.abs(ke - ke1) / ke1) < 1e-5
+    assert rel_l2(np.stack(out[:3], axis=1), np.stack(out1[:3], axis=1)) < 1e-5
     # whole tiles do not go through the split/combine path: after ONE step (same inputs) their
     # bodies are bitwise equal to the unsplit run (later steps see the tail's rounding)
     w = info["whole_tiles"] * info["threads"] * info["bodies_per_thread"]
@@ -363,9 +363,12 @@ def test_full_size_c3_plummer_properties(nbx, oracle):
     # (ver2 arithmetic and j order) for the same bodies: the GPU must be as close to the truth.
     ref32 = oracle.acc_f32(s, sel)
     err_ref = np.linalg.norm(ref32 - truth, axis=1) / tn
-    assert np.median(err) < 2e-5
-    assert np.max(err) < max(1e-4, 2.0 * np.max(err_ref))
-    assert np.linalg.norm(acc[sel] - ref32) / np.linalg.norm(ref32) < max(1e-4, 2.0 * np.linalg.norm(ref32 - truth) / np.linalg.norm(truth))
+    d_ref = np.linalg.norm(acc[sel] - ref32, axis=1) / tn
+    print(f"\nC3 sampled forces vs fp64: GPU median {np.median(err):.2e} max {np.max(err):.2e}; "
+          f"reference float median {np.median(err_ref):.2e} max {np.max(err_ref):.2e}; GPU vs reference float max {np.max(d_ref):.2e}")
+    assert np.median(err) < max(2e-5, 1.5 * np.median(err_ref))
+    assert np.max(err) < max(1e-4, 1.5 * np.max(err_ref))
+    assert np.max(d_ref) < max(1e-4, 2.0 * np.max(err_ref))
     dt = np.float32(0.1)
     for k in range(3):
         assert np.allclose(out[3 + k], arrs[3 + k] + acc[:, k] * dt, rtol=1e-6, atol=1e-9)
