@@ -273,6 +273,32 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                 const float4 q1 = rec[2 * (jr + u) + 1];
                 const float2 xj = make_float2(q0.x, q0.y), yj = make_float2(q0.z, q0.w);
                 const float2 zj = make_float2(q1.x, q1.y), mj = make_float2(q1.z, q1.w);
+                if (MATH & 16) {
+                    // stage-major source order (all subtracts, then all r^2, ...): same arithmetic
+                    float2 dx[R], dy[R], dz[R], sv[R];
+#pragma unroll
+                    for (int b = 0; b < R; ++b) { dx[b] = __fadd2_rn(xj, nx[b]); dy[b] = __fadd2_rn(yj, ny[b]); dz[b] = __fadd2_rn(zj, nz[b]); }
+#pragma unroll
+                    for (int b = 0; b < R; ++b) sv[b] = __ffma2_rn(dx[b], dx[b], eps2v);
+#pragma unroll
+                    for (int b = 0; b < R; ++b) sv[b] = __ffma2_rn(dy[b], dy[b], sv[b]);
+#pragma unroll
+                    for (int b = 0; b < R; ++b) sv[b] = __ffma2_rn(dz[b], dz[b], sv[b]);
+#pragma unroll
+                    for (int b = 0; b < R; ++b) sv[b] = make_float2(rsqrt_approx(sv[b].x), rsqrt_approx(sv[b].y));
+#pragma unroll
+                    for (int b = 0; b < R; ++b) {
+                        const float2 inv2 = __fmul2_rn(sv[b], sv[b]);
+                        const float2 mi = __fmul2_rn(mj, sv[b]);
+                        sv[b] = __fmul2_rn(inv2, mi);
+                    }
+#pragma unroll
+                    for (int b = 0; b < R; ++b) {
+                        ax[b] = __ffma2_rn(dx[b], sv[b], ax[b]);
+                        ay[b] = __ffma2_rn(dy[b], sv[b], ay[b]);
+                        az[b] = __ffma2_rn(dz[b], sv[b], az[b]);
+                    }
+                } else
 #pragma unroll
                 for (int b = 0; b < R; ++b) {
                     // MATH bit set = that op group is issued as scalar instead of packed instructions
