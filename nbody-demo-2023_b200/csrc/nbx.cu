@@ -405,7 +405,15 @@ static int step_exchange(nbx_ctx *c)
         st = c->comm_stream;
     }
     NC(g_nccl.AllGather(buf + c->i_begin, buf, (size_t)c->i_count * 4, ncclFloat, c->comm, st));
-    if (c->exchange == NBX_EXCHANGE_NCCL_OVERLAP) {
+    return NBX_OK;
+}
+
+// After the collective has really been enqueued (i.e. after ncclGroupEnd when one thread drives
+// several GPUs -- inside a group the call above is only recorded): mark the point the next step's
+// remote-shard launch has to wait for.
+static int step_exchange_mark(nbx_ctx *c)
+{
+    if (c->world > 1 && c->exchange == NBX_EXCHANGE_NCCL_OVERLAP) {
         CU(cudaEventRecord(c->ev_gather, c->comm_stream));
         c->gather_pending = true;
     }
@@ -461,6 +469,7 @@ static int enqueue_steps(nbx_ctx *c, int nsteps)
         int rc = step_compute(c);
         if (rc) return rc;
         if ((rc = step_exchange(c))) return rc;
+        if ((rc = step_exchange_mark(c))) return rc;
         --left;
     }
     return NBX_OK;
@@ -735,6 +744,10 @@ int nbx_run_group(nbx_ctx **ctxs, int count, int nsteps, double *kenergy_out, do
                     if ((rc = step_exchange(ctxs[g]))) { g_nccl.GroupEnd(); return rc; }
                 }
                 NC(g_nccl.GroupEnd());
+                for (int g = 0; g < count; ++g) {
+                    CU(cudaSetDevice(ctxs[g]->device));
+                    if ((rc = step_exchange_mark(ctxs[g]))) return rc;
+                }
             }
         }
         for (int g = 0; g < count; ++g) {            // kinetic energy is summed on the host below
