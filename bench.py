@@ -256,16 +256,17 @@ def main():
             ctx.download(*out)
             return ke[0]
         e2e_step()
+        e2e_steps = min(args.steps, 5)         # same per-step work every time; keeps long runs bounded
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(e2e_steps):
             e2e_step()
         torch.cuda.synchronize(); dist.barrier()
         te = dist.reduce_scalar(time.perf_counter() - t0, "max")
         i_count = info1["i_count"]
-        e2e = {"value": round(pairs_per_step * args.steps / te / 1e9, 3), "unit": "G pair-interactions/s",
+        e2e = {"value": round(pairs_per_step * e2e_steps / te / 1e9, 3), "unit": "G pair-interactions/s", "steps": e2e_steps,
                "h2d_bytes_per_step": 7 * 4 * n, "d2h_bytes_per_step": 3 * 4 * n + 3 * 4 * min(i_count, n) + 8,
-               "ms_per_step": round(1e3 * te / args.steps, 3),
+               "ms_per_step": round(1e3 * te / e2e_steps, 3),
                "what": "nbx_upload(7 host SoA arrays, pinned) + nbx_run(1) + nbx_download(pos, vel) per step, per rank"}
 
     if rank != 0:
