@@ -259,8 +259,18 @@ def test_full_size_c2_properties(nbx, oracle):
         setattr(s, f, a)
     sel = np.random.default_rng(7).choice(n, 512, replace=False).astype(np.int32)
     truth = oracle.acc_fp64(s, sel)
-    err = np.linalg.norm(acc[sel] - truth, axis=1) / np.linalg.norm(truth, axis=1)
-    assert np.max(err) < 1e-4
+    tn = np.linalg.norm(truth, axis=1)
+    err = np.linalg.norm(acc[sel] - truth, axis=1) / tn
+    # a million float terms per body: float arithmetic itself sits ~1e-4 from the fp64 force.  The
+    # bar is the reference's own float result (ver2 arithmetic, same j order) for the same bodies.
+    ref32 = oracle.acc_f32(s, sel)
+    err_ref = np.linalg.norm(ref32 - truth, axis=1) / tn
+    d_ref = np.linalg.norm(acc[sel] - ref32, axis=1) / tn
+    print(f"\nC2 sampled forces vs fp64: GPU median {np.median(err):.2e} max {np.max(err):.2e}; "
+          f"reference float median {np.median(err_ref):.2e} max {np.max(err_ref):.2e}; GPU vs reference float max {np.max(d_ref):.2e}")
+    assert np.median(err) < max(2e-5, 1.5 * np.median(err_ref))
+    assert np.max(err) < max(1e-4, 1.5 * np.max(err_ref))
+    assert np.max(d_ref) < max(1e-4, 2.0 * np.max(err_ref))
     dt = np.float32(0.1)
     for k in range(3):
         v_new = arrs[3 + k] + acc[:, k] * dt
