@@ -121,3 +121,25 @@ def test_ver5_all_cli_refuses_cpu_share(pkg):
     r = subprocess.run([pkg.CLI_ALL_PATH, "64", "2", "cpu"], capture_output=True, text=True)
     assert r.returncode == 1 and "GPU-only" in r.stderr
     assert r.stdout.splitlines()[0] == "cpu"          # ver5_all/main.cpp:42 echoes the selector first
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 with no C++ or CUDA types, and a
+    C program must link against libnbx.so (symbols unmangled)."""
+    import importlib
+    pkg = importlib.import_module("nbody-demo-2023_b200")
+    hdr = os.path.join(REPO, "include", "nbx.h")
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = tmp_path / "t.c"
+    src.write_text('#include "nbx.h"\n#include <stdio.h>\nint main(void){ int n = -1; nbx_ctx *c = 0;'
+                   ' if (nbx_abi_version() != NBX_ABI_VERSION) return 2; if (nbx_device_count(&n)) return 3;'
+                   ' if (n == 0 && nbx_create(&c, 16, 0, 0, 1, 0.1f, 6.67259e-11f, 1e-3f) != NBX_ERR_NODEVICE) return 4;'
+                   ' if (c) nbx_destroy(c); printf("%d %s\\n", n, nbx_last_error()); return 0; }\n')
+    exe = tmp_path / "t"
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe),
+                        "-L", pkg.PKG_DIR, "-lnbx", "-Wl,-rpath," + pkg.PKG_DIR], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
