@@ -293,7 +293,7 @@ def main():
         "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "n_bodies": n, "pairs_per_step": pairs_per_step,
-                   "parallelism": f"i-shard x{args.gpus}" + (f", exchange={args.exchange}" if args.gpus > 1 else ""),
+                   "parallelism": f"i-shard x{args.gpus}" + (f", exchange={ {0: 'nccl', 1: 'p2p', 2: 'nccl_overlap'}[ctx.exchange_used] }" if args.gpus > 1 else ""),
                    "kernel_shape": nbx.variant_names()[info1["variant"]],
                    "i_tiles": info1["i_tiles"], "whole_tiles": info1["whole_tiles"], "j_splits": info1["j_splits"], "ctas_per_sm": info1["ctas_per_sm"],
                    "l2": "flushed between timed steps (256 MiB memset); positions (16 B/body) are L2-resident by design within a step",

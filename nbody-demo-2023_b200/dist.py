@@ -79,14 +79,35 @@ def barrier():
 
 def make_sharded_context(nbx, n: int, exchange: int, device: int | None = None, **ctx_kw):
     """Create this rank's nbx.Context (i-shard rank/world) and wire the exchange:
-    NCCL unique id broadcast from rank 0, and for P2P the all-gather of handle blobs."""
+    NCCL unique id broadcast from rank 0, and for P2P the all-gather of handle blobs.
+    If ANY rank cannot map its peers' buffers (no peer access / IPC in this container), every
+    rank switches to the NCCL all-gather together -- both are GPU paths; `ctx.exchange_used`
+    says which one runs."""
     rank, local_rank, world = env_world()
     ctx = nbx.Context(n, device=local_rank if device is None else device, rank=rank, world=world, **ctx_kw)
+    ctx.exchange_used = exchange if world > 1 else None
     if world > 1:
         ctx.set_option("exchange", exchange)
         uid = nbx.comm_unique_id() if rank == 0 else None
         uid = broadcast_bytes(uid, nbx.UNIQUE_ID_BYTES, src=0)
         ctx.comm_init(uid)
         if exchange == nbx.EXCHANGE_P2P:
-            ctx.p2p_attach(all_gather_bytes(ctx.p2p_export()))
+            ok = 1.0
+            try:
+                blob = ctx.p2p_export()
+            except nbx.NbxError as e:
+                ok, blob, why = 0.0, bytes(nbx.P2P_BLOB_BYTES), str(e)
+            blobs = all_gather_bytes(blob)
+            if reduce_scalar(ok, "min") > 0:
+                try:
+                    ctx.p2p_attach(blobs)
+                except nbx.NbxError as e:
+                    ok, why = 0.0, str(e)
+            if reduce_scalar(ok, "min") == 0:
+                if rank == 0:
+                    import sys
+                    print(f"nbx: P2P exchange unavailable on at least one rank ({why if ok == 0 else 'peer'}); "
+                          f"all ranks use the NCCL all-gather", file=sys.stderr)
+                ctx.set_option("exchange", nbx.EXCHANGE_NCCL)
+                ctx.exchange_used = nbx.EXCHANGE_NCCL
     return ctx
