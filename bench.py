@@ -117,8 +117,19 @@ def cpu_baseline_block(budget_s: float = 12.0):
     n_s = 131072 if rate0 > 20 else 65536
     steps = int(max(1, min(40, round(budget_s * rate0 * 1e9 / float(n_s) ** 2))))
     rate, kind, cores, secs = cpu_reference_rate(n_s, steps)
+    others = {}
+    try:   # the north star's other two reported baselines, same box, same run (a few seconds in total)
+        from oracle import oracle as O
+        if O.ref_available("ver0"):
+            _, _, s0 = O.ref_run("ver0", 2000, 50, threads=1)
+            others["ver0_1_thread_n2000"] = round(2000.0 ** 2 * 50 / s0 / 1e9, 4)
+        if O.ref_available("ver7"):
+            _, _, s7 = O.ref_run("ver7", 16384, 20, threads=cores)
+            others[f"ver7_{cores}_threads_n16384"] = round(16384.0 ** 2 * 20 / s7 / 1e9, 3)
+    except Exception as ex:
+        others["error"] = repr(ex)
     return {"value": round(rate, 3), "unit": "G pair-interactions/s", "cores": cores, "kind": kind,
-            "gflops_ref_convention": round(rate * 29.0, 1),
+            "gflops_ref_convention": round(rate * 29.0, 1), "other_reference_versions": others,
             "sample": f"{'oracle/_ref ver8 (OpenMP+SIMD+i-tiling, unmodified reference sources)' if kind == 'reference' else 'oracle port of ver7'}"
                       f", N={n_s}, {steps} steps, {secs:.1f} s step-loop time, OMP_NUM_THREADS={cores}; pairs/s is flat in N for O(N^2)"}
 
