@@ -96,6 +96,7 @@ NBX_API void nbx_destroy(nbx_ctx *ctx);
 /* Tuning / mode knobs; all optional, call before the first nbx_run.
  *   "j_splits"  >=1 force a j-split count, 0 = auto (fills the SMs at small N)
  *   "graph"     1/0 replay steps from a CUDA graph (auto: on for small N)
+ *   "accurate"  1/0 two-level accumulation (float per j tile, then double): large-N accuracy option
  *   "pdl"       1/0 programmatic dependent launch between consecutive steps (-1 = auto: many-wave grids only)
  *   "exchange"  NBX_EXCHANGE_*
  *   "variant"   index into the compiled kernel-shape table (see nbx_variant_name), -1 = auto */

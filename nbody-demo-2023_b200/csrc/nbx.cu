@@ -110,7 +110,7 @@ struct Variant {
 template <int R2, int THREADS, int TJ, int STAGES, int UNROLL, int MINB, int MATH = 0>
 static Variant make_variant(const char *name)
 {
-    return Variant{name, R2, THREADS, TJ, STAGES, UNROLL, MINB, nbx::step_smem_bytes<THREADS, TJ, STAGES>(),
+    return Variant{name, R2, THREADS, TJ, STAGES, UNROLL, MINB, nbx::step_smem_bytes<THREADS, TJ, STAGES, R2, MATH>(),
                    (const void *)nbx::step_kernel<R2, THREADS, TJ, STAGES, UNROLL, MINB, MATH>};
 }
 
@@ -121,6 +121,7 @@ static const std::vector<Variant> &variants()
         // order of the inner loop (+1% over body-major in same-box A/B, profiles/r01_ab_*.log)
         make_variant<2, 256, 256, 4, 4, 2, 16>("r4_t256_u4_stage"),   // [0] default for large shards (kLargeVariant)
         make_variant<1, 128, 256, 4, 4, 6>("r2_t128_u4"),             // [1] default for small shards (kSmallVariant)
+        make_variant<2, 256, 256, 4, 4, 2, 48>("r4_t256_u4_stage_acc64"),   // [2] accuracy option (kAccurateVariant)
         make_variant<2, 256, 256, 4, 2, 2>("r4_t256_u2"),
         make_variant<2, 256, 256, 4, 2, 2, 16>("r4_t256_u2_stage"),
         make_variant<2, 256, 256, 4, 4, 2>("r4_t256_u4"),
@@ -137,7 +138,7 @@ static const std::vector<Variant> &variants()
     return v;
 }
 
-constexpr int kLargeVariant = 0, kSmallVariant = 1;
+constexpr int kLargeVariant = 0, kSmallVariant = 1, kAccurateVariant = 2;
 constexpr int kSmallShardBodies = 8192;   // below this the 256-body CTAs of kSmallVariant fill the SMs better
 
 // ------------------------------------------------------------------------------
@@ -166,7 +167,7 @@ struct nbx_ctx {
     bool uploaded = false;
 
     // configuration
-    int variant = 0, opt_variant = -1, opt_splits = 0, opt_graph = -1, opt_pdl = -1, exchange = NBX_EXCHANGE_NCCL;
+    int variant = 0, opt_variant = -1, opt_splits = 0, opt_graph = -1, opt_pdl = -1, opt_accurate = 0, exchange = NBX_EXCHANGE_NCCL;
     bool resolved = false;
     int i_tiles = 0, whole_tiles = 0, j_splits = 1, split_bodies = 0, ctas_per_sm = 0, use_graph = 0;
 
@@ -207,7 +208,9 @@ static int pick_splits(int tiles, int j_len, int sms)
 static int resolve(nbx_ctx *c)
 {
     if (c->resolved) return NBX_OK;
-    c->variant = c->opt_variant >= 0 ? c->opt_variant : (c->i_count < kSmallShardBodies ? kSmallVariant : kLargeVariant);
+    c->variant = c->opt_variant >= 0 ? c->opt_variant
+                 : c->opt_accurate   ? kAccurateVariant
+                                     : (c->i_count < kSmallShardBodies ? kSmallVariant : kLargeVariant);
     const Variant &v = variants()[c->variant];
     CU(cudaSetDevice(c->device));
     CU(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
@@ -585,6 +588,8 @@ int nbx_set_option(nbx_ctx *c, const char *key, long long value)
         c->opt_splits = (int)value;
     } else if (k == "graph") {
         c->opt_graph = value < 0 ? -1 : (value ? 1 : 0);
+    } else if (k == "accurate") {
+        c->opt_accurate = value ? 1 : 0;
     } else if (k == "pdl") {
         c->opt_pdl = value < 0 ? -1 : (value ? 1 : 0);
     } else if (k == "exchange") {

@@ -13,6 +13,7 @@
 //   NBODY_IC=uniform|plummer  initial positions (default: the reference's uniform cube)
 //   NBODY_DUMP=file     write the final state (NBXD format, see oracle/ref_harness.cpp)
 //   NBODY_RESTORE=file  start from a state written by NBODY_DUMP instead of the initial conditions
+//   NBODY_ACCURATE=1    two-level (float, then double) force accumulation: large-N accuracy option
 //   NBODY_VARIANT=i, NBODY_JSPLITS=s, NBODY_GRAPH=0|1   kernel-shape knobs
 #include "GSimulation.hpp"
 
@@ -145,6 +146,7 @@ void GSimulation::start()
         if (std::getenv("NBODY_VARIANT") && nbx_set_option(ctx[g], "variant", env_int("NBODY_VARIANT", 0))) die("variant");
         if (std::getenv("NBODY_JSPLITS") && nbx_set_option(ctx[g], "j_splits", env_int("NBODY_JSPLITS", 0))) die("j_splits");
         if (std::getenv("NBODY_GRAPH") && nbx_set_option(ctx[g], "graph", env_int("NBODY_GRAPH", -1))) die("graph");
+        if (std::getenv("NBODY_ACCURATE") && nbx_set_option(ctx[g], "accurate", env_int("NBODY_ACCURATE", 0))) die("accurate");
         if (nbx_set_option(ctx[g], "exchange", exchange)) die("exchange");
         if (nbx_upload(ctx[g], particles->pos_x.data(), particles->pos_y.data(), particles->pos_z.data(),
                        particles->vel_x.data(), particles->vel_y.data(), particles->vel_z.data(),

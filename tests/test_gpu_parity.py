@@ -427,3 +427,30 @@ def test_pdl_and_graph_combinations_are_bitwise_identical(nbx):
                 assert np.array_equal(ke, base[0])
                 for a, b in zip(out, base[1]):
                     assert np.array_equal(a, b)
+
+
+def test_accurate_option(nbx, oracle):
+    """"accurate" folds the float lane sums into doubles after every j tile: at N = 1 M the sampled
+    forces must come out far closer to the fp64 truth than the reference's own float result, and
+    small cases must still agree with the oracle."""
+    arrs = nbx.ic(3000)
+    ke, out, info = gpu_run(nbx, arrs, 5, accurate=1)
+    assert nbx.variant_names()[info["variant"]].endswith("acc64")
+    s = oracle.ic_uniform(3000)
+    ke_o = oracle.run(s, 5, variant="ver2")
+    assert np.max(np.abs(ke - ke_o) / ke_o) < KE_TOL
+    assert rel_l2(np.stack(out[:3], axis=1), s.pos()) < POS_TOL
+    n = 1 << 20
+    arrs = nbx.ic(n)
+    with nbx.Context(n) as c:
+        c.set_option("accurate", 1)
+        c.upload(*arrs)
+        acc = c.accelerations()
+    st = oracle.State(n)
+    for f, a in zip(oracle.State.FIELDS, arrs):
+        setattr(st, f, a)
+    sel = np.random.default_rng(7).choice(n, 256, replace=False).astype(np.int32)
+    truth = oracle.acc_fp64(st, sel)
+    err = np.linalg.norm(acc[sel] - truth, axis=1) / np.linalg.norm(truth, axis=1)
+    print(f"\naccurate option, N = 1 M sampled forces vs fp64: median {np.median(err):.2e} max {np.max(err):.2e}")
+    assert np.max(err) < 1e-5
