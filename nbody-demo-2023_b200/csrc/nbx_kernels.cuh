@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     double *red = reinterpret_cast<double *>(empty + STAGES);
     int *s_flag = reinterpret_cast<int *>(red + WARPS);
     // acc64 (MATH & 32): accuracy option.  Each thread folds its float lane sums into
-    // a double per (body, component) after every j tile, so no float sum is longer than TJ/2 terms:
+    // a double per (body, component) after every 4th j tile, so no float sum is longer than 2*TJ terms:
     // the large-N float summation error (1e-4 at 1 M, 1e-3 at 4 M for the reference's single
     // accumulator) drops to the 1e-6 level for ~1% time.  hi[q * THREADS + tid]: conflict-free.
     double *hi = reinterpret_cast<double *>(smem_raw + step_smem_bytes<THREADS, TJ, STAGES>());
@@ -328,11 +328,11 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                 }
             }
         }
-        if (MATH & 32) {
+        if ((MATH & 32) && ((t & 3) == 3 || t == ntiles - 1)) {   // every 4th tile and the last one
 #pragma unroll
             for (int b = 0; b < R; ++b) {
                 double *h = hi + (3 * b) * THREADS + tid;
-                const bool first = (t == 0);
+                const bool first = (t <= 3);
                 h[0] = (first ? 0.0 : h[0]) + ((double)ax[b].x + (double)ax[b].y);
                 h[THREADS] = (first ? 0.0 : h[THREADS]) + ((double)ay[b].x + (double)ay[b].y);
                 h[2 * THREADS] = (first ? 0.0 : h[2 * THREADS]) + ((double)az[b].x + (double)az[b].y);
