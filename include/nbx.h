@@ -102,6 +102,11 @@ NBX_API void nbx_destroy(nbx_ctx *ctx);
  *   "variant"   index into the compiled kernel-shape table (see nbx_variant_name), -1 = auto */
 NBX_API int nbx_set_option(nbx_ctx *ctx, const char *key, long long value);
 NBX_API int nbx_get_info(const nbx_ctx *ctx, nbx_info *out);
+/* The launch plan nbx_run would use for shard `rank` of `world` on a GPU with `sm_count` SMs --
+ * padding, shard, kernel shape, unsplit tiles, j-split count -- without touching a device
+ * (host arithmetic only; fills the planning fields of nbx_info).  variant/j_splits: -1/0 = auto. */
+NBX_API int nbx_plan(int n, int rank, int world, int sm_count, int exchange, long long variant,
+                     long long j_splits, nbx_info *out);
 NBX_API int nbx_variant_count(void);
 NBX_API const char *nbx_variant_name(int idx);
 

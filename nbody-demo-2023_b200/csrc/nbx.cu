@@ -205,21 +205,22 @@ static int pick_splits(int tiles, int j_len, int sms)
     return splits;
 }
 
-static int resolve(nbx_ctx *c)
+// The launch plan of one shard: kernel shape, i-tiles, which tiles run unsplit, j-split counts.
+// Pure host arithmetic (no CUDA calls) so that nbx_plan() can expose it to CPU-only tests.
+struct Plan {
+    int variant, i_tiles, whole_tiles, j_splits, split_bodies, s_local, s_remote, use_graph;
+};
+
+static Plan make_plan(int n_pad, int i_count, int world, int sm_count, int exchange, int opt_variant,
+                      int opt_accurate, int opt_splits, int opt_graph)
 {
-    if (c->resolved) return NBX_OK;
-    c->variant = c->opt_variant >= 0 ? c->opt_variant
-                 : c->opt_accurate   ? kAccurateVariant
-                                     : (c->i_count < kSmallShardBodies ? kSmallVariant : kLargeVariant);
-    const Variant &v = variants()[c->variant];
-    CU(cudaSetDevice(c->device));
-    CU(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, v.threads, v.smem));
-    if (occ < 1) return fail(NBX_ERR_CUDA, "kernel variant %s cannot be resident", v.name);
-    c->ctas_per_sm = occ;
+    Plan p{};
+    p.variant = opt_variant >= 0 ? opt_variant
+                : opt_accurate   ? kAccurateVariant
+                                 : (i_count < kSmallShardBodies ? kSmallVariant : kLargeVariant);
+    const Variant &v = variants()[p.variant];
     const int bi = v.threads * v.r2 * 2;
-    c->i_tiles = (c->i_count + bi - 1) / bi;
+    p.i_tiles = (i_count + bi - 1) / bi;
 
     // j-split.  CTAs are dealt round-robin to the SMs, so a group of t equal tiles cut S ways costs
     //   ceil(t*S / SMs) rounds x (fixed cost per CTA + n_pad/S j-bodies) + S partials to combine.
@@ -228,37 +229,58 @@ static int resolve(nbx_ctx *c)
     // Tiles that fill whole rounds of the SM count run unsplit (no partial-force traffic); only
     // the tail -- everything, when there are fewer tiles than SMs -- is split.  A forced
     // "j_splits" applies to every tile (that is what makes results shard-count independent).
-    int splits = c->opt_splits;
-    c->whole_tiles = 0;
-    const bool overlap = c->world > 1 && c->exchange == NBX_EXCHANGE_NCCL_OVERLAP;
+    int splits = opt_splits;
+    p.whole_tiles = 0;
+    p.s_local = p.s_remote = 1;
+    const bool overlap = world > 1 && exchange == NBX_EXCHANGE_NCCL_OVERLAP;
     if (overlap) {
         // a step is two launches: the own j-shard (no remote data needed), then the other shards
         // once their all-gather has landed; every tile is split, partials of both launches meet
         // in the last-arriver combine of the second one.
-        c->s_local = splits > 0 ? splits : pick_splits(c->i_tiles, c->i_count, c->sm_count);
-        c->s_remote = splits > 0 ? splits : pick_splits(c->i_tiles, c->n_pad - c->i_count, c->sm_count);
-        splits = c->s_local + c->s_remote;
+        p.s_local = splits > 0 ? splits : pick_splits(p.i_tiles, i_count, sm_count);
+        p.s_remote = splits > 0 ? splits : pick_splits(p.i_tiles, n_pad - i_count, sm_count);
+        splits = p.s_local + p.s_remote;
     } else if (splits <= 0) {
         // Unsplit tiles only when they fill >= 3 whole rounds of the SMs.  The first wave is not
         // dealt evenly (traced at 152 tiles: 6 of 148 SMs received two whole-tile CTAs, 6 none) and
         // co-resident CTAs do not share an SM fairly (the older one runs, the newer one starves),
         // so with 1-2 rounds of long CTAs the step took 2x; from 3 rounds on the short tail CTAs
         // even it out (profiles/r01_hybrid_probe.log).
-        const int rounds = c->i_tiles / c->sm_count;
-        c->whole_tiles = rounds >= 3 ? rounds * c->sm_count : 0;
-        const int tail = c->i_tiles - c->whole_tiles;
-        splits = tail > 0 ? pick_splits(tail, c->n_pad, c->sm_count) : 1;
+        const int rounds = p.i_tiles / sm_count;
+        p.whole_tiles = rounds >= 3 ? rounds * sm_count : 0;
+        const int tail = p.i_tiles - p.whole_tiles;
+        splits = tail > 0 ? pick_splits(tail, n_pad, sm_count) : 1;
     }
-    splits = std::max(1, std::min(splits, std::max(1, c->n_pad / 8)));
-    c->j_splits = splits;
-    if (splits == 1) c->whole_tiles = c->i_tiles;
-    c->split_bodies = std::max(0, c->i_count - c->whole_tiles * bi);
+    splits = std::max(1, std::min(splits, std::max(1, n_pad / 8)));
+    p.j_splits = splits;
+    if (splits == 1) p.whole_tiles = p.i_tiles;
+    p.split_bodies = std::max(0, i_count - p.whole_tiles * bi);
 
-    if (c->opt_graph >= 0)
-        c->use_graph = c->opt_graph;
+    if (opt_graph >= 0)
+        p.use_graph = opt_graph;
     else   // launch latency matters below ~1 ms per step
-        c->use_graph = ((double)c->n_pad * (double)c->i_count < 2.5e9) ? 1 : 0;
-    if (c->world > 1 && c->exchange != NBX_EXCHANGE_P2P) c->use_graph = 0;
+        p.use_graph = ((double)n_pad * (double)i_count < 2.5e9) ? 1 : 0;
+    if (world > 1 && exchange != NBX_EXCHANGE_P2P) p.use_graph = 0;
+    return p;
+}
+
+static int resolve(nbx_ctx *c)
+{
+    if (c->resolved) return NBX_OK;
+    const Plan pl = make_plan(c->n_pad, c->i_count, c->world, c->sm_count, c->exchange, c->opt_variant,
+                              c->opt_accurate, c->opt_splits, c->opt_graph);
+    c->variant = pl.variant;
+    c->i_tiles = pl.i_tiles; c->whole_tiles = pl.whole_tiles; c->j_splits = pl.j_splits;
+    c->split_bodies = pl.split_bodies; c->s_local = pl.s_local; c->s_remote = pl.s_remote;
+    c->use_graph = pl.use_graph;
+    const int splits = pl.j_splits;
+    const Variant &v = variants()[c->variant];
+    CU(cudaSetDevice(c->device));
+    CU(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, v.threads, v.smem));
+    if (occ < 1) return fail(NBX_ERR_CUDA, "kernel variant %s cannot be resident", v.name);
+    c->ctas_per_sm = occ;
 
     if (c->part) { CU(cudaFree(c->part)); c->part = nullptr; }
     if (c->tile_ticket) { CU(cudaFree(c->tile_ticket)); c->tile_ticket = nullptr; }
@@ -493,6 +515,26 @@ int nbx_device_count(int *count)
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
     *count = n;
+    return NBX_OK;
+}
+
+int nbx_plan(int n, int rank, int world, int sm_count, int exchange, long long variant, long long j_splits,
+             nbx_info *out)
+{
+    if (!out) return fail(NBX_ERR_ARG, "out is NULL");
+    if (n < 1 || world < 1 || world > nbx::kMaxWorld || rank < 0 || rank >= world || sm_count < 1)
+        return fail(NBX_ERR_ARG, "bad n/rank/world/sm_count");
+    if (variant < -1 || variant >= (long long)variants().size()) return fail(NBX_ERR_ARG, "variant out of range");
+    const int n_pad = round_up(n, 8 * world), i_count = n_pad / world;
+    const Plan pl = make_plan(n_pad, i_count, world, sm_count, exchange, (int)variant, 0, (int)j_splits, -1);
+    const Variant &v = variants()[pl.variant];
+    std::memset(out, 0, sizeof *out);
+    out->abi_version = NBX_ABI_VERSION;
+    out->sm_count = sm_count; out->n = n; out->n_pad = n_pad; out->rank = rank; out->world = world;
+    out->i_begin = rank * i_count; out->i_count = i_count;
+    out->threads = v.threads; out->bodies_per_thread = 2 * v.r2; out->tile_bodies = v.tj; out->stages = v.stages;
+    out->i_tiles = pl.i_tiles; out->whole_tiles = pl.whole_tiles; out->j_splits = pl.j_splits;
+    out->use_graph = pl.use_graph; out->exchange = exchange; out->variant = pl.variant;
     return NBX_OK;
 }
 

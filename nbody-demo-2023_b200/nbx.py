@@ -23,7 +23,7 @@ P2P_BLOB_BYTES = 256
 # every symbol include/nbx.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "nbx_abi_version", "nbx_last_error", "nbx_device_count", "nbx_create", "nbx_destroy",
-    "nbx_set_option", "nbx_get_info", "nbx_variant_count", "nbx_variant_name", "nbx_upload",
+    "nbx_set_option", "nbx_get_info", "nbx_plan", "nbx_variant_count", "nbx_variant_name", "nbx_upload",
     "nbx_download", "nbx_run", "nbx_accelerations", "nbx_simulate", "nbx_comm_unique_id",
     "nbx_comm_init", "nbx_comm_init_all", "nbx_run_group", "nbx_p2p_export", "nbx_p2p_attach",
     "nbx_ic_uniform", "nbx_ic_plummer", "nbx_gflop_per_step", "nbx_host_alloc", "nbx_host_free",
@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
         L.nbx_destroy.restype = None
         L.nbx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
         L.nbx_get_info.argtypes = [C.c_void_p, C.POINTER(Info)]
+        L.nbx_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.POINTER(Info)]
         L.nbx_upload.argtypes = [C.c_void_p] + [_f32p] * 7
         L.nbx_download.argtypes = [C.c_void_p] + [_f32p] * 6
         L.nbx_run.argtypes = [C.c_void_p, C.c_int, _f64p, _f64p]
@@ -113,6 +114,14 @@ def device_count() -> int:
 def variant_names():
     L = lib()
     return [L.nbx_variant_name(i).decode() for i in range(L.nbx_variant_count())]
+
+
+def plan(n: int, rank: int = 0, world: int = 1, sm_count: int = 148, exchange: int = EXCHANGE_NCCL,
+         variant: int = -1, j_splits: int = 0) -> dict:
+    """nbx_plan: the launch plan for a shard, computed on the host (no GPU needed)."""
+    i = Info()
+    _check(lib().nbx_plan(n, rank, world, sm_count, exchange, variant, j_splits, C.byref(i)))
+    return i.as_dict()
 
 
 def gflop_per_step(n: int) -> float:

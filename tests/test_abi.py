@@ -143,3 +143,44 @@ def test_header_is_plain_c(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+
+
+def test_launch_plan_host_logic(nbx):
+    """nbx_plan is the host-side decomposition nbx_run uses (no device needed)."""
+    names = nbx.variant_names()
+    # BASELINE configs on a 148-SM B200
+    c0 = nbx.plan(2000)
+    assert names[c0["variant"]] == "r2_t128_u4" and c0["i_tiles"] == 8 and c0["whole_tiles"] == 0 and c0["j_splits"] > 1
+    assert c0["use_graph"] == 1 and c0["n_pad"] == 2000
+    c1 = nbx.plan(16384)
+    assert names[c1["variant"]] == "r4_t256_u4_stage" and (c1["i_tiles"], c1["whole_tiles"], c1["j_splits"]) == (16, 0, 9)
+    assert c1["use_graph"] == 1
+    c2 = nbx.plan(1 << 20)
+    assert (c2["i_tiles"], c2["whole_tiles"]) == (1024, 888) and c2["j_splits"] >= 13 and c2["use_graph"] == 0
+    mid = nbx.plan(262144)                       # 256 tiles = 1.7 SM rounds: no unsplit tiles
+    assert mid["whole_tiles"] == 0 and mid["j_splits"] > 1
+    for r in range(8):                           # C3 strong scaling, 8 ranks
+        c3 = nbx.plan(1 << 22, rank=r, world=8, exchange=nbx.EXCHANGE_P2P)
+        assert c3["i_begin"] == r * (1 << 19) and c3["i_count"] == 1 << 19
+        assert (c3["i_tiles"], c3["whole_tiles"]) == (512, 444)
+    ov = nbx.plan(1 << 22, rank=3, world=8, exchange=nbx.EXCHANGE_NCCL_OVERLAP)
+    assert ov["whole_tiles"] == 0 and ov["j_splits"] >= 2 and ov["use_graph"] == 0
+    # invariants over many sizes / worlds / SM counts
+    for sm in (148, 132, 64):
+        for world in (1, 2, 4, 8):
+            for n in (1, 9, 1000, 8191, 8192, 100000, 151552, 155648, 303104, 454656, 1 << 20, (1 << 22) + 5):
+                p = nbx.plan(n, rank=world - 1, world=world, sm_count=sm)
+                bi = p["threads"] * p["bodies_per_thread"]
+                assert p["n_pad"] % (8 * world) == 0 and 0 <= p["n_pad"] - n < 8 * world
+                assert p["i_tiles"] == -(-p["i_count"] // bi)
+                assert p["whole_tiles"] % sm == 0 or p["whole_tiles"] == p["i_tiles"]
+                assert p["whole_tiles"] in (0, p["i_tiles"]) or p["whole_tiles"] // sm >= 3
+                assert 1 <= p["j_splits"] <= max(1, p["n_pad"] // 8)
+                if p["j_splits"] == 1:
+                    assert p["whole_tiles"] == p["i_tiles"]
+    forced = nbx.plan(1 << 20, j_splits=4)
+    assert forced["whole_tiles"] == 0 and forced["j_splits"] == 4      # a pinned split applies to every tile
+    with pytest.raises(nbx.NbxError):
+        nbx.plan(0)
+    with pytest.raises(nbx.NbxError):
+        nbx.plan(100, rank=2, world=2)
