@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define NBX_ABI_VERSION 1
+#define NBX_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NBX_API __attribute__((visibility("default")))
@@ -39,13 +39,21 @@ enum {
     NBX_ERR_CUDA = 2,     /* a CUDA runtime/driver call failed              */
     NBX_ERR_NCCL = 3,     /* an NCCL call failed / NCCL not available       */
     NBX_ERR_STATE = 4,    /* call sequence error (e.g. run before upload)   */
-    NBX_ERR_NODEVICE = 5  /* no usable sm_100 device                        */
+    NBX_ERR_NODEVICE = 5, /* no usable sm_100 device                        */
+    NBX_ERR_PEER = 6,     /* multi-GPU: a peer GPU did not finish its step within "peer_timeout_ms",
+                             or the run was aborted; the context is poisoned -- destroy it */
+    NBX_ERR_DEBUG = 7     /* debug build (libnbx_debug.so) only: a device-side index/ticket
+                             check failed; nbx_last_error() names the source line          */
 };
 
-/* How updated positions reach the other GPUs after each step (multi-GPU only). */
+/* How updated positions reach the other GPUs after each step (multi-GPU only).
+ * ONE default everywhere (library, nbody.x, bench.py): NBX_EXCHANGE_P2P.  It needs the peers'
+ * buffers mapped (nbx_p2p_attach; nbx_run_group does it by itself inside one process); where
+ * that is impossible (no peer access / no CUDA IPC) the callers in this repo fall back to
+ * NBX_EXCHANGE_NCCL on all ranks together (dist.make_sharded_context, GSimulation::start). */
 enum {
     NBX_EXCHANGE_NCCL = 0, /* ncclAllGather of the updated shard (stream ordered)          */
-    NBX_EXCHANGE_P2P = 1,  /* the force kernel's epilogue stores each updated body straight
+    NBX_EXCHANGE_P2P = 1,  /* DEFAULT: the force kernel's epilogue stores each updated body straight
                               into every peer's replica over NVLink; flags replace the collective */
     NBX_EXCHANGE_NCCL_OVERLAP = 2 /* ncclAllGather on a side stream, hidden behind the next step's
                               force work on the rank's own j-shard (a step = two launches)   */
@@ -75,6 +83,9 @@ typedef struct nbx_info {
     long long aux_launches;      /* pack/unpack/other launches since create           */
     double last_run_seconds;     /* device time of the last nbx_run (CUDA events)     */
     double kernel_seconds_total; /* device time summed over every nbx_run             */
+    int device_error;       /* last device error word (0 = none): low byte 1 = peer timeout
+                               (peer rank << 8), 2 = aborted, 3 = debug check (source line << 8) */
+    int peer_timeout_ms;    /* bound on the in-kernel wait for a peer's previous step */
 } nbx_info;
 
 /* ---- library ---------------------------------------------------------------- */
@@ -98,7 +109,9 @@ NBX_API void nbx_destroy(nbx_ctx *ctx);
  *   "graph"     1/0 replay steps from a CUDA graph (auto: on for small N)
  *   "accurate"  1/0 two-level accumulation (float per j tile, then double): large-N accuracy option
  *   "pdl"       1/0 programmatic dependent launch between consecutive steps (-1 = auto: many-wave grids only)
- *   "exchange"  NBX_EXCHANGE_*
+ *   "exchange"  NBX_EXCHANGE_* (default NBX_EXCHANGE_P2P)
+ *   "peer_timeout_ms"  P2P exchange: how long a step may wait inside the kernel for a peer GPU to
+ *               finish the previous step before the run fails with NBX_ERR_PEER (default 30000)
  *   "variant"   index into the compiled kernel-shape table (see nbx_variant_name), -1 = auto */
 NBX_API int nbx_set_option(nbx_ctx *ctx, const char *key, long long value);
 NBX_API int nbx_get_info(const nbx_ctx *ctx, nbx_info *out);
@@ -118,10 +131,26 @@ NBX_API const char *nbx_variant_name(int idx);
  * all positions and masses and the velocities of its own shard.
  * download replaces the D2H at cuda/Compute.cu:164-166: positions of all n bodies
  * and velocities of this context's shard only ([i_begin, i_begin+i_count) of
- * vx/vy/vz are written, the rest is left untouched). */
+ * vx/vy/vz are written, the rest is left untouched).
+ * In a multi-process job every rank must have returned from nbx_upload before any rank's
+ * nbx_run starts stepping: nbx_run enforces it with an in-stream NCCL barrier when a communicator
+ * exists; without one (P2P exchange, nbx_comm_init never called) the host must barrier itself. */
 NBX_API int nbx_upload(nbx_ctx *ctx, const float *px, const float *py, const float *pz,
                const float *vx, const float *vy, const float *vz, const float *mass);
 NBX_API int nbx_download(nbx_ctx *ctx, float *px, float *py, float *pz,
+                 float *vx, float *vy, float *vz);
+/* Sharded variants for multi-GPU jobs: the same FULL caller-owned arrays are passed, but each
+ * context moves only its own i-shard over PCIe (28 B/body of the shard up, 24 B/body down) --
+ * the reference's MPI code ships every array to every rank each step
+ * (ver5_all/GSimulation.cpp:170-189).  upload_sharded is COLLECTIVE (every rank calls it; the
+ * packed records are then all-gathered GPU-to-GPU with ncclAllGather, so it needs nbx_comm_init
+ * first); upload_group is its one-process form (peer copies between the contexts' GPUs, NCCL
+ * not needed).  download_shard writes only [i_begin, i_begin+i_count) of all six arrays. */
+NBX_API int nbx_upload_sharded(nbx_ctx *ctx, const float *px, const float *py, const float *pz,
+               const float *vx, const float *vy, const float *vz, const float *mass);
+NBX_API int nbx_upload_group(nbx_ctx **ctxs, int count, const float *px, const float *py, const float *pz,
+               const float *vx, const float *vy, const float *vz, const float *mass);
+NBX_API int nbx_download_shard(nbx_ctx *ctx, float *px, float *py, float *pz,
                  float *vx, float *vy, float *vz);
 
 /* ---- the hot path -------------------------------------------------------------
@@ -131,7 +160,10 @@ NBX_API int nbx_download(nbx_ctx *ctx, float *px, float *py, float *pz,
  * (all shards: the multi-GPU sum is taken inside), may be NULL.  seconds_out =
  * device time of the loop (CUDA events on the launching stream), may be NULL.
  * Blocks until the steps are done.  In a multi-process job every rank calls it
- * with the same nsteps. */
+ * with the same nsteps.  P2P exchange without a communicator (nbx_comm_init never called):
+ * kenergy_out holds THIS shard's part of the sum and the caller adds the ranks' values.
+ * A peer that stops stepping makes the call fail with NBX_ERR_PEER after "peer_timeout_ms"
+ * instead of hanging; the context is then poisoned (every later call fails the same way). */
 NBX_API int nbx_run(nbx_ctx *ctx, int nsteps, double *kenergy_out, double *seconds_out);
 
 /* Accelerations only (no update): a_i for this context's shard from the current
@@ -154,7 +186,10 @@ NBX_API int nbx_simulate(int n, int nsteps, float dt, float G, float eps2,
  *    nbx_run_group drives them together.
  * P2P exchange needs the peers' buffers mapped: nbx_p2p_export gives an opaque
  * blob (NBX_P2P_BLOB_BYTES), the host all-gathers the blobs, nbx_p2p_attach maps
- * them (cudaIpc* across processes, direct peer access inside one process). */
+ * them (cudaIpc* across processes, direct peer access inside one process).
+ * nbx_run_group with the (default) P2P exchange attaches its contexts by itself and needs no
+ * communicator at all; if a GPU cannot reach a peer it switches every context to the NCCL
+ * all-gather (then nbx_comm_init_all must have been called). */
 #define NBX_UNIQUE_ID_BYTES 128
 #define NBX_P2P_BLOB_BYTES 256
 NBX_API int nbx_comm_unique_id(void *id_out);

@@ -122,18 +122,25 @@ static const std::vector<Variant> &variants()
         make_variant<2, 256, 256, 4, 4, 2, 16>("r4_t256_u4_stage"),   // [0] default for large shards (kLargeVariant)
         make_variant<1, 128, 256, 4, 4, 6>("r2_t128_u4"),             // [1] default for small shards (kSmallVariant)
         make_variant<2, 256, 256, 4, 4, 2, 48>("r4_t256_u4_stage_acc64"),   // [2] accuracy option (kAccurateVariant)
+        // CTA sizes the ver5_all-style CLI can ask for (argv[5] = thread_dim0, cuda/Compute.cu:137-145)
+        make_variant<2, 128, 256, 4, 2, 4>("r4_t128_u2"),
+        make_variant<2, 512, 512, 4, 2, 1>("r4_t512_u2"),
+        make_variant<2, 64, 128, 4, 2, 8>("r4_t64_u2"),
+#ifdef NBX_ABLATION
+        // Shapes kept only for the tuning tools (tools/sweep.py, tools/ab.py): `make ablation`
+        // builds libnbx_ablation.so with them; the product library does not carry them.
         make_variant<2, 256, 256, 4, 2, 2>("r4_t256_u2"),
         make_variant<2, 256, 256, 4, 2, 2, 16>("r4_t256_u2_stage"),
         make_variant<2, 256, 256, 4, 4, 2>("r4_t256_u4"),
         make_variant<2, 256, 256, 4, 1, 2>("r4_t256_u1"),
-        make_variant<2, 128, 256, 4, 2, 4>("r4_t128_u2"),
-        make_variant<2, 512, 512, 4, 2, 1>("r4_t512_u2"),
-        make_variant<2, 64, 128, 4, 2, 8>("r4_t64_u2"),
         make_variant<3, 256, 256, 4, 2, 2>("r6_t256_u2"),
         make_variant<4, 256, 256, 4, 1, 1>("r8_t256_u1"),
         make_variant<1, 256, 256, 4, 4, 3>("r2_t256_u4"),
-        make_variant<2, 256, 256, 4, 2, 2, 1>("r4_t256_u2_sacc"),     // ablation: scalar accumulate
-        make_variant<2, 256, 256, 4, 2, 2, 15>("r4_t256_u2_scalar"),  // ablation: no packed FP32 at all
+        make_variant<2, 256, 256, 4, 2, 2, 1>("r4_t256_u2_sacc"),     // scalar accumulate
+        make_variant<2, 256, 256, 4, 2, 2, 15>("r4_t256_u2_scalar"),  // no packed FP32 at all
+        make_variant<2, 256, 256, 4, 2, 3, 16>("r4_t256_u2_stage_occ3"),   // 3 CTAs/SM x 85 registers
+        make_variant<2, 256, 256, 4, 1, 3, 16>("r4_t256_u1_stage_occ3"),
+#endif
     };
     return v;
 }
@@ -158,7 +165,7 @@ struct nbx_ctx {
     float4 *acc = nullptr;
     int *tile_ticket = nullptr;
     double *ke_part = nullptr;
-    int *counters = nullptr;   // [0]=ke_ticket [1]=dev_step [2]=dev_epoch
+    int *counters = nullptr;   // [0]=ke_ticket [1]=dev_step [2]=dev_epoch [3]=dev_err [4]=barrier word
     int *flags = nullptr;      // [kMaxWorld] peers publish their epoch here
     double *ke_dev = nullptr;
     int ke_cap = 0;
@@ -167,7 +174,11 @@ struct nbx_ctx {
     bool uploaded = false;
 
     // configuration
-    int variant = 0, opt_variant = -1, opt_splits = 0, opt_graph = -1, opt_pdl = -1, opt_accurate = 0, exchange = NBX_EXCHANGE_NCCL;
+    int variant = 0, opt_variant = -1, opt_splits = 0, opt_graph = -1, opt_pdl = -1, opt_accurate = 0;
+    int exchange = NBX_EXCHANGE_P2P;   // the one default (include/nbx.h); callers fall back to NCCL together
+    int peer_timeout_ms = 30000;
+    int device_error = 0;              // last value read from counters[3]; non-zero = poisoned
+    bool debug_fault = false;          // debug build only
     bool resolved = false;
     int i_tiles = 0, whole_tiles = 0, j_splits = 1, split_bodies = 0, ctas_per_sm = 0, use_graph = 0;
 
@@ -309,7 +320,10 @@ static void fill_params(const nbx_ctx *c, StepParams &p, int in_buf, float4 *acc
     p.ke_ticket = c->counters + 0;
     p.dev_step = c->counters + 1;
     p.dev_epoch = c->counters + 2;
+    p.dev_err = c->counters + 3;
     p.ke_out = c->ke_dev;
+    p.ke_cap = c->debug_fault ? 0 : c->ke_cap;
+    p.peer_wait_ns = (unsigned long long)c->peer_timeout_ms * 1000000ull;
     p.acc_out = acc_out;
     p.n_pad = c->n_pad;
     p.i_begin = c->i_begin;
@@ -525,6 +539,9 @@ int nbx_plan(int n, int rank, int world, int sm_count, int exchange, long long v
     if (n < 1 || world < 1 || world > nbx::kMaxWorld || rank < 0 || rank >= world || sm_count < 1)
         return fail(NBX_ERR_ARG, "bad n/rank/world/sm_count");
     if (variant < -1 || variant >= (long long)variants().size()) return fail(NBX_ERR_ARG, "variant out of range");
+    if (exchange != NBX_EXCHANGE_NCCL && exchange != NBX_EXCHANGE_P2P && exchange != NBX_EXCHANGE_NCCL_OVERLAP)
+        return fail(NBX_ERR_ARG, "unknown exchange %d", exchange);
+    if (j_splits < 0 || j_splits > 4096) return fail(NBX_ERR_ARG, "j_splits out of range");
     const int n_pad = round_up(n, 8 * world), i_count = n_pad / world;
     const Plan pl = make_plan(n_pad, i_count, world, sm_count, exchange, (int)variant, 0, (int)j_splits, -1);
     const Variant &v = variants()[pl.variant];
@@ -589,8 +606,8 @@ int nbx_create(nbx_ctx **out, int n, int device, int rank, int world, float dt, 
     CUB(cudaMalloc(&c->pos[0], (size_t)c->n_pad * sizeof(float4)));
     CUB(cudaMalloc(&c->pos[1], (size_t)c->n_pad * sizeof(float4)));
     CUB(cudaMalloc(&c->vel, (size_t)c->i_count * sizeof(float4)));
-    CUB(cudaMalloc(&c->counters, 4 * sizeof(int)));
-    CUB(cudaMemset(c->counters, 0, 4 * sizeof(int)));
+    CUB(cudaMalloc(&c->counters, 8 * sizeof(int)));
+    CUB(cudaMemset(c->counters, 0, 8 * sizeof(int)));
     CUB(cudaMalloc(&c->flags, nbx::kMaxWorld * sizeof(int)));
     CUB(cudaMemset(c->flags, 0, nbx::kMaxWorld * sizeof(int)));
 #undef CUB
@@ -638,6 +655,16 @@ int nbx_set_option(nbx_ctx *c, const char *key, long long value)
         if (value != NBX_EXCHANGE_NCCL && value != NBX_EXCHANGE_P2P && value != NBX_EXCHANGE_NCCL_OVERLAP)
             return fail(NBX_ERR_ARG, "unknown exchange %lld", value);
         c->exchange = (int)value;
+    } else if (k == "peer_timeout_ms") {
+        if (value < 1 || value > 3600000) return fail(NBX_ERR_ARG, "peer_timeout_ms out of range");
+        c->peer_timeout_ms = (int)value;
+        if (c->graph2) { cudaGraphExecDestroy(c->graph2); c->graph2 = nullptr; }     // baked into graph nodes
+        if (c->graph16) { cudaGraphExecDestroy(c->graph16); c->graph16 = nullptr; }
+        return NBX_OK;
+#ifdef NBX_DEBUG
+    } else if (k == "debug_fault") {   // fault injection for tests/test_gpu_debug_build.py: the kernel is told
+        c->debug_fault = value != 0;   // it has no energy slots, so its slot check fires (the store stays valid)
+#endif
     } else if (k == "variant") {
         if (value < -1 || value >= (long long)variants().size()) return fail(NBX_ERR_ARG, "variant out of range");
         c->opt_variant = (int)value;
@@ -662,6 +689,7 @@ int nbx_get_info(const nbx_ctx *c, nbx_info *o)
     o->use_graph = c->use_graph; o->exchange = c->exchange; o->variant = c->variant;
     o->kernel_launches = c->kernel_launches; o->aux_launches = c->aux_launches;
     o->last_run_seconds = c->last_run_seconds; o->kernel_seconds_total = c->kernel_seconds_total;
+    o->device_error = c->device_error; o->peer_timeout_ms = c->peer_timeout_ms;
     return NBX_OK;
 }
 
@@ -675,83 +703,250 @@ static int ensure_stage(nbx_ctx *c, size_t floats)
     return NBX_OK;
 }
 
+// H2D of bodies [lo, hi) of the caller's seven arrays into the staging buffer + pack into pos[0]
+// (and pos[1] when `both`) and vel.  Leaves the work on c->stream (no sync).
+static int stage_and_pack(nbx_ctx *c, const float *const src[7], int lo, int hi, int rec_begin, int rec_count, bool both)
+{
+    CU(cudaSetDevice(c->device));
+    const size_t cnt = (size_t)std::max(hi - lo, 0);
+    int rc = ensure_stage(c, 7 * std::max(cnt, (size_t)1));
+    if (rc) return rc;
+    if (cnt)
+        for (int k = 0; k < 7; ++k)
+            CU(cudaMemcpyAsync(c->stage + k * cnt, src[k] + lo, cnt * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (rec_count > 0) {
+        nbx::pack_kernel<<<(rec_count + 255) / 256, 256, 0, c->stream>>>(c->stage, (int)cnt, lo, c->n, rec_begin, rec_count,
+                                                                         c->i_begin, c->i_count, c->G, c->pos[0],
+                                                                         both ? c->pos[1] : nullptr, c->vel);
+        CU(cudaGetLastError());
+        c->aux_launches++;
+    }
+    return NBX_OK;
+}
+
+static void mark_uploaded(nbx_ctx *c)
+{
+    c->cur = 0;
+    c->gather_pending = false;
+    c->uploaded = true;
+}
+
 int nbx_upload(nbx_ctx *c, const float *px, const float *py, const float *pz,
                const float *vx, const float *vy, const float *vz, const float *mass)
 {
     if (!c || !px || !py || !pz || !vx || !vy || !vz || !mass) return fail(NBX_ERR_ARG, "NULL argument");
-    CU(cudaSetDevice(c->device));
-    const size_t n = (size_t)c->n;
-    int rc = ensure_stage(c, 7 * n);
-    if (rc) return rc;
     const float *src[7] = {px, py, pz, vx, vy, vz, mass};
-    for (int k = 0; k < 7; ++k)
-        CU(cudaMemcpyAsync(c->stage + k * n, src[k], n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    const int recs = c->n_pad / 2;
-    nbx::pack_kernel<<<(recs + 255) / 256, 256, 0, c->stream>>>(c->stage, c->n, c->n_pad, c->i_begin, c->i_count,
-                                                                c->G, c->pos[0], c->pos[1], c->vel);
+    int rc = stage_and_pack(c, src, 0, c->n, 0, c->n_pad / 2, true);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    mark_uploaded(c);
+    return NBX_OK;
+}
+
+// This shard's slice of the caller's arrays and its records (the padding tail belongs to the last shard).
+static void shard_span(const nbx_ctx *c, int *lo, int *hi)
+{
+    *lo = std::min(c->i_begin, c->n);
+    *hi = std::min(c->i_begin + c->i_count, c->n);
+}
+
+int nbx_upload_sharded(nbx_ctx *c, const float *px, const float *py, const float *pz,
+                       const float *vx, const float *vy, const float *vz, const float *mass)
+{
+    if (!c || !px || !py || !pz || !vx || !vy || !vz || !mass) return fail(NBX_ERR_ARG, "NULL argument");
+    if (c->world == 1) return nbx_upload(c, px, py, pz, vx, vy, vz, mass);
+    if (!c->comm) return fail(NBX_ERR_STATE, "nbx_upload_sharded needs nbx_comm_init first (it all-gathers the packed shards)");
+    const float *src[7] = {px, py, pz, vx, vy, vz, mass};
+    int lo, hi;
+    shard_span(c, &lo, &hi);
+    int rc = stage_and_pack(c, src, lo, hi, c->i_begin / 2, c->i_count / 2, false);
+    if (rc) return rc;
+    // packed records of every shard, GPU to GPU (16 B/body over NVLink instead of 28 B/body over PCIe)
+    NC(g_nccl.AllGather(c->pos[0] + c->i_begin, c->pos[0], (size_t)c->i_count * 4, ncclFloat, c->comm, c->stream));
+    CU(cudaMemcpyAsync(c->pos[1], c->pos[0], (size_t)c->n_pad * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    mark_uploaded(c);
+    return NBX_OK;
+}
+
+int nbx_upload_group(nbx_ctx **ctxs, int count, const float *px, const float *py, const float *pz,
+                     const float *vx, const float *vy, const float *vz, const float *mass)
+{
+    if (!ctxs || count < 1 || !px || !py || !pz || !vx || !vy || !vz || !mass) return fail(NBX_ERR_ARG, "NULL argument");
+    for (int g = 0; g < count; ++g)
+        if (!ctxs[g] || ctxs[g]->world != count || ctxs[g]->rank != g || ctxs[g]->n != ctxs[0]->n)
+            return fail(NBX_ERR_ARG, "ctxs[%d] is not rank %d of %d", g, g, count);
+    if (count == 1) return nbx_upload(ctxs[0], px, py, pz, vx, vy, vz, mass);
+    const float *src[7] = {px, py, pz, vx, vy, vz, mass};
+    int rc;
+    // peer copies need peer access; where a pair cannot be enabled every context uploads in full
+    bool peers_ok = true;
+    for (int g = 0; g < count && peers_ok; ++g)
+        for (int h = 0; h < count && peers_ok; ++h) {
+            if (ctxs[g]->device == ctxs[h]->device) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, ctxs[g]->device, ctxs[h]->device) != cudaSuccess || !can) peers_ok = false;
+        }
+    cudaGetLastError();
+    if (!peers_ok) {
+        for (int g = 0; g < count; ++g)
+            if ((rc = nbx_upload(ctxs[g], px, py, pz, vx, vy, vz, mass))) return rc;
+        return NBX_OK;
+    }
+    for (int g = 0; g < count; ++g) {
+        int lo, hi;
+        shard_span(ctxs[g], &lo, &hi);
+        if ((rc = stage_and_pack(ctxs[g], src, lo, hi, ctxs[g]->i_begin / 2, ctxs[g]->i_count / 2, false))) return rc;
+    }
+    for (int g = 0; g < count; ++g) {          // owner g pushes its packed shard into every other replica
+        nbx_ctx *c = ctxs[g];
+        CU(cudaSetDevice(c->device));
+        for (int h = 0; h < count; ++h) {
+            if (h == g) continue;
+            CU(cudaMemcpyPeerAsync(ctxs[h]->pos[0] + c->i_begin, ctxs[h]->device, c->pos[0] + c->i_begin, c->device,
+                                   (size_t)c->i_count * sizeof(float4), c->stream));
+        }
+    }
+    for (int g = 0; g < count; ++g) {
+        CU(cudaSetDevice(ctxs[g]->device));
+        CU(cudaStreamSynchronize(ctxs[g]->stream));
+    }
+    for (int g = 0; g < count; ++g) {
+        nbx_ctx *c = ctxs[g];
+        CU(cudaSetDevice(c->device));
+        CU(cudaMemcpyAsync(c->pos[1], c->pos[0], (size_t)c->n_pad * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    for (int g = 0; g < count; ++g) {
+        CU(cudaSetDevice(ctxs[g]->device));
+        CU(cudaStreamSynchronize(ctxs[g]->stream));
+        mark_uploaded(ctxs[g]);
+    }
+    return NBX_OK;
+}
+
+// positions of bodies [plo, phi) and velocities of [vlo, vhi) -> the caller's arrays (same offsets)
+static int unpack_and_copy(nbx_ctx *c, int plo, int phi, float *px, float *py, float *pz, float *vx, float *vy, float *vz)
+{
+    if (!c->uploaded) return fail(NBX_ERR_STATE, "download before upload");
+    CU(cudaSetDevice(c->device));
+    const size_t cnt = (size_t)std::max(phi - plo, 0);
+    if (cnt == 0) return NBX_OK;
+    int rc = ensure_stage(c, 7 * cnt);
+    if (rc) return rc;
+    nbx::unpack_kernel<<<((int)cnt + 255) / 256, 256, 0, c->stream>>>(c->pos[c->cur], c->vel, (int)cnt, plo, (int)cnt,
+                                                                      c->i_begin, c->i_count, c->stage);
     CU(cudaGetLastError());
     c->aux_launches++;
+    float *dst[3] = {px, py, pz};
+    for (int k = 0; k < 3; ++k)
+        if (dst[k]) CU(cudaMemcpyAsync(dst[k] + plo, c->stage + k * cnt, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    const size_t lo = (size_t)std::max(std::min(c->i_begin, c->n), plo);
+    const size_t hi = (size_t)std::min(std::min(c->i_begin + c->i_count, c->n), phi);
+    float *vdst[3] = {vx, vy, vz};
+    for (int k = 0; k < 3; ++k)
+        if (vdst[k] && hi > lo)
+            CU(cudaMemcpyAsync(vdst[k] + lo, c->stage + (3 + k) * cnt + (lo - plo), (hi - lo) * sizeof(float),
+                               cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->cur = 0;
-    c->gather_pending = false;
-    c->uploaded = true;
     return NBX_OK;
 }
 
 int nbx_download(nbx_ctx *c, float *px, float *py, float *pz, float *vx, float *vy, float *vz)
 {
     if (!c) return fail(NBX_ERR_ARG, "NULL context");
-    if (!c->uploaded) return fail(NBX_ERR_STATE, "download before upload");
-    CU(cudaSetDevice(c->device));
-    const size_t n = (size_t)c->n;
-    int rc = ensure_stage(c, 7 * n);
-    if (rc) return rc;
-    nbx::unpack_kernel<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->pos[c->cur], c->vel, c->n, c->i_begin,
-                                                                  c->i_count, c->stage);
-    CU(cudaGetLastError());
-    c->aux_launches++;
-    float *dst[3] = {px, py, pz};
-    for (int k = 0; k < 3; ++k)
-        if (dst[k]) CU(cudaMemcpyAsync(dst[k], c->stage + k * n, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    const size_t lo = (size_t)std::min(c->i_begin, c->n);
-    const size_t hi = (size_t)std::min(c->i_begin + c->i_count, c->n);
-    float *vdst[3] = {vx, vy, vz};
-    for (int k = 0; k < 3; ++k)
-        if (vdst[k] && hi > lo)
-            CU(cudaMemcpyAsync(vdst[k] + lo, c->stage + (3 + k) * n + lo, (hi - lo) * sizeof(float),
-                               cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    return NBX_OK;
+    return unpack_and_copy(c, 0, c->n, px, py, pz, vx, vy, vz);
 }
 
-static int check_runnable(nbx_ctx *c, int nsteps)
+int nbx_download_shard(nbx_ctx *c, float *px, float *py, float *pz, float *vx, float *vy, float *vz)
+{
+    if (!c) return fail(NBX_ERR_ARG, "NULL context");
+    int lo, hi;
+    shard_span(c, &lo, &hi);
+    return unpack_and_copy(c, lo, hi, px, py, pz, vx, vy, vz);
+}
+
+static int device_error_code(nbx_ctx *c, int word)
+{
+    c->device_error = word;
+    const int kind = word & 0xff, detail = word >> 8;
+    if (kind == nbx::kDevErrPeerTimeout)
+        return fail(NBX_ERR_PEER, "rank %d: peer rank %d did not finish its step within %d ms (P2P exchange); context poisoned",
+                    c->rank, detail, c->peer_timeout_ms);
+    if (kind == nbx::kDevErrHostAbort) return fail(NBX_ERR_PEER, "rank %d: run aborted; context poisoned", c->rank);
+    if (kind == nbx::kDevErrDebugCheck)
+        return fail(NBX_ERR_DEBUG, "device-side check failed at nbx_kernels.cuh:%d; context poisoned", detail);
+    return fail(NBX_ERR_CUDA, "unknown device error word %d", word);
+}
+
+static int check_runnable(nbx_ctx *c, int nsteps, bool group)
 {
     if (!c) return fail(NBX_ERR_ARG, "NULL context");
     if (nsteps < 0) return fail(NBX_ERR_ARG, "nsteps must be >= 0");
+    if (c->device_error) return device_error_code(c, c->device_error);
     if (!c->uploaded) return fail(NBX_ERR_STATE, "run before upload");
     if (c->world > 1) {
-        if (!c->comm) return fail(NBX_ERR_STATE, "world > 1 needs nbx_comm_init / nbx_comm_init_all first");
-        if (c->exchange == NBX_EXCHANGE_P2P && !c->p2p_ready)
-            return fail(NBX_ERR_STATE, "P2P exchange needs nbx_p2p_attach first");
+        if (c->exchange == NBX_EXCHANGE_P2P) {
+            if (!c->p2p_ready && !group)
+                return fail(NBX_ERR_STATE, "P2P exchange (the default) needs nbx_p2p_attach first; or set \"exchange\" to NBX_EXCHANGE_NCCL");
+        } else if (!c->comm) {
+            return fail(NBX_ERR_STATE, "NCCL exchange needs nbx_comm_init / nbx_comm_init_all first");
+        }
     }
     return NBX_OK;
 }
 
+// Host-side abort: make every queued or spinning step of this context return (the kernels poll the
+// error word), then drain its streams.  Used when a multi-GPU enqueue fails half way.
+static void poison(nbx_ctx *c)
+{
+    if (!c || !c->counters) return;
+    cudaSetDevice(c->device);
+    static const int word = nbx::kDevErrHostAbort;
+    cudaMemcpyAsync(c->counters + 3, &word, sizeof(int), cudaMemcpyHostToDevice, c->comm_stream);
+    cudaStreamSynchronize(c->comm_stream);
+    cudaStreamSynchronize(c->stream);
+    if (!c->device_error) c->device_error = word;
+    cudaGetLastError();
+}
+
+// After the steps have been synchronised: did the device report a peer timeout / failed check?
+static int read_device_error(nbx_ctx *c)
+{
+#ifndef NBX_DEBUG
+    if (!(c->world > 1 && c->exchange == NBX_EXCHANGE_P2P)) return NBX_OK;   // nothing can set it
+#endif
+    int word = 0;
+    CU(cudaMemcpy(&word, c->counters + 3, sizeof(int), cudaMemcpyDeviceToHost));
+    return word ? device_error_code(c, word) : NBX_OK;
+}
+
 int nbx_run(nbx_ctx *c, int nsteps, double *kenergy_out, double *seconds_out)
 {
-    int rc = check_runnable(c, nsteps);
+    int rc = check_runnable(c, nsteps, false);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
     if ((rc = resolve(c))) return rc;
     if ((rc = ensure_ke(c, nsteps))) return rc;
+    const bool p2p = c->world > 1 && c->exchange == NBX_EXCHANGE_P2P;
+    if (p2p && c->comm) {
+        // In-stream barrier: no rank starts stepping before every rank has enqueued this run (and so has
+        // finished its nbx_upload: a peer's epilogue stores into OUR replica) -- and the in-kernel
+        // peer wait then only ever covers the skew between GPUs that ARE stepping.
+        NC(g_nccl.AllReduce(c->counters + 4, c->counters + 4, 1, ncclInt, ncclSum, c->comm, c->stream));
+    }
     CU(cudaMemsetAsync(c->counters + 1, 0, sizeof(int), c->stream));   // dev_step = 0
     CU(cudaEventRecord(c->ev0, c->stream));
-    if ((rc = enqueue_steps(c, nsteps))) return rc;
-    if ((rc = finish_run(c, nsteps, true))) return rc;
+    if ((rc = enqueue_steps(c, nsteps)) || (rc = finish_run(c, nsteps, c->comm != nullptr))) {
+        const std::string why = g_err;
+        poison(c);
+        g_err = why;
+        return rc;
+    }
     CU(cudaEventRecord(c->ev1, c->stream));
     if (kenergy_out && nsteps > 0)
         CU(cudaMemcpyAsync(kenergy_out, c->ke_dev, (size_t)nsteps * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if ((rc = read_device_error(c))) return rc;
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->last_run_seconds = ms * 1e-3;
@@ -760,13 +955,46 @@ int nbx_run(nbx_ctx *c, int nsteps, double *kenergy_out, double *seconds_out)
     return NBX_OK;
 }
 
+// One process, several GPUs: map every context's replicas and flags into every other context.
+static int attach_group(nbx_ctx **ctxs, int count)
+{
+    std::vector<unsigned char> blobs((size_t)count * NBX_P2P_BLOB_BYTES);
+    int rc;
+    for (int g = 0; g < count; ++g)
+        if ((rc = nbx_p2p_export(ctxs[g], blobs.data() + (size_t)g * NBX_P2P_BLOB_BYTES))) return rc;
+    for (int g = 0; g < count; ++g)
+        if ((rc = nbx_p2p_attach(ctxs[g], blobs.data()))) return rc;
+    return NBX_OK;
+}
+
 int nbx_run_group(nbx_ctx **ctxs, int count, int nsteps, double *kenergy_out, double *seconds_out)
 {
     if (!ctxs || count < 1) return fail(NBX_ERR_ARG, "bad context array");
     int rc;
     for (int g = 0; g < count; ++g) {
-        if ((rc = check_runnable(ctxs[g], nsteps))) return rc;
-        if (ctxs[g]->world != count || ctxs[g]->rank != g) return fail(NBX_ERR_ARG, "ctxs[%d] is not rank %d of %d", g, g, count);
+        if ((rc = check_runnable(ctxs[g], nsteps, true))) return rc;
+        const nbx_ctx *a = ctxs[g], *b = ctxs[0];
+        if (a->world != count || a->rank != g) return fail(NBX_ERR_ARG, "ctxs[%d] is not rank %d of %d", g, g, count);
+        if (a->n != b->n || a->exchange != b->exchange || a->opt_splits != b->opt_splits || a->opt_variant != b->opt_variant ||
+            a->opt_accurate != b->opt_accurate || a->dt != b->dt || a->G != b->G || a->eps2 != b->eps2)
+            return fail(NBX_ERR_ARG, "ctxs[%d] differs from ctxs[0] in n / exchange / j_splits / variant / accurate / constants", g);
+    }
+    if (count > 1 && ctxs[0]->exchange == NBX_EXCHANGE_P2P) {
+        bool ready = true;
+        for (int g = 0; g < count; ++g) ready = ready && ctxs[g]->p2p_ready;
+        if (!ready && attach_group(ctxs, count) != NBX_OK) {
+            // no peer access between some pair: every context takes the NCCL all-gather instead
+            const std::string why = g_err;
+            for (int g = 0; g < count; ++g) {
+                if (!ctxs[g]->comm)
+                    return fail(NBX_ERR_STATE, "P2P exchange unavailable (%s) and no communicator for the NCCL fallback: call nbx_comm_init_all",
+                                why.c_str());
+                ctxs[g]->exchange = NBX_EXCHANGE_NCCL;
+                ctxs[g]->resolved = false;
+            }
+        }
+    }
+    for (int g = 0; g < count; ++g) {
         CU(cudaSetDevice(ctxs[g]->device));
         if ((rc = resolve(ctxs[g]))) return rc;
         if ((rc = ensure_ke(ctxs[g], nsteps))) return rc;
@@ -774,10 +1002,9 @@ int nbx_run_group(nbx_ctx **ctxs, int count, int nsteps, double *kenergy_out, do
         CU(cudaEventRecord(ctxs[g]->ev0, ctxs[g]->stream));
     }
     const bool nccl_x = count > 1 && ctxs[0]->exchange != NBX_EXCHANGE_P2P;
-    if (count == 1) {
-        if ((rc = enqueue_steps(ctxs[0], nsteps))) return rc;
-    } else {
-        // step-major order: with the P2P exchange a GPU's step s+1 spins until every peer has
+    auto enqueue_all = [&]() -> int {
+        if (count == 1) return enqueue_steps(ctxs[0], nsteps);
+        // step-major order: with the P2P exchange a GPU's step s+1 waits until every peer has
         // finished step s, so no GPU may be queued far ahead of the others by this one thread.
         for (int s = 0; s < nsteps; ++s) {
             for (int g = 0; g < count; ++g) {
@@ -801,15 +1028,26 @@ int nbx_run_group(nbx_ctx **ctxs, int count, int nsteps, double *kenergy_out, do
             CU(cudaSetDevice(ctxs[g]->device));
             if ((rc = finish_run(ctxs[g], nsteps, false))) return rc;
         }
+        return NBX_OK;
+    };
+    if ((rc = enqueue_all())) {
+        // work may be queued on some GPUs and not on others: abort all of it, leave no kernel spinning
+        const std::string why = g_err;
+        for (int g = 0; g < count; ++g) poison(ctxs[g]);
+        g_err = why;
+        return rc;
     }
     std::vector<double> tmp((size_t)std::max(nsteps, 1));
     if (kenergy_out) std::fill(kenergy_out, kenergy_out + nsteps, 0.0);
     double tmax = 0.0;
+    int first_err = NBX_OK;
+    std::string first_why;
     for (int g = 0; g < count; ++g) {
         nbx_ctx *c = ctxs[g];
         CU(cudaSetDevice(c->device));
         CU(cudaEventRecord(c->ev1, c->stream));
         CU(cudaStreamSynchronize(c->stream));
+        if ((rc = read_device_error(c)) && first_err == NBX_OK) { first_err = rc; first_why = g_err; }
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         c->last_run_seconds = ms * 1e-3;
@@ -820,6 +1058,7 @@ int nbx_run_group(nbx_ctx **ctxs, int count, int nsteps, double *kenergy_out, do
             for (int s = 0; s < nsteps; ++s) kenergy_out[s] += tmp[s];   // rank order: deterministic
         }
     }
+    if (first_err) { g_err = first_why; return first_err; }
     if (seconds_out) *seconds_out = tmax;
     return NBX_OK;
 }
@@ -832,11 +1071,17 @@ int nbx_accelerations(nbx_ctx *c, float *ax, float *ay, float *az)
     int rc = resolve(c);
     if (rc) return rc;
     if (!c->acc) CU(cudaMalloc(&c->acc, (size_t)c->i_count * sizeof(float4)));
+    if ((rc = ensure_ke(c, 1))) return rc;
     if ((rc = launch_step(c, c->cur, c->acc))) return rc;
-    std::vector<float4> h((size_t)c->i_count);
-    CU(cudaMemcpyAsync(h.data(), c->acc, h.size() * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    const size_t cnt = (size_t)c->i_count;
+    if ((rc = ensure_stage(c, 3 * cnt))) return rc;
+    nbx::acc_soa_kernel<<<((int)cnt + 255) / 256, 256, 0, c->stream>>>(c->acc, (int)cnt, c->stage);
+    CU(cudaGetLastError());
+    c->aux_launches++;
+    float *dst[3] = {ax, ay, az};
+    for (int k = 0; k < 3; ++k)
+        CU(cudaMemcpyAsync(dst[k], c->stage + k * cnt, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < c->i_count; ++i) { ax[i] = h[i].x; ay[i] = h[i].y; az[i] = h[i].z; }
     return NBX_OK;
 }
 
@@ -875,6 +1120,7 @@ int nbx_comm_init(nbx_ctx *c, const void *id_bytes)
     CU(cudaSetDevice(c->device));
     ncclUniqueId id;
     std::memcpy(&id, id_bytes, sizeof id);
+    if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }   // re-initialisation replaces the old one
     NC(g_nccl.CommInitRank(&c->comm, c->world, id, c->rank));
     return NBX_OK;
 }
@@ -890,6 +1136,8 @@ int nbx_comm_init_all(nbx_ctx **ctxs, int count)
         if (!ctxs[g] || ctxs[g]->world != count || ctxs[g]->rank != g) return fail(NBX_ERR_ARG, "ctxs[%d] is not rank %d of %d", g, g, count);
         devs[g] = ctxs[g]->device;
     }
+    for (int g = 0; g < count; ++g)
+        if (ctxs[g]->comm) { g_nccl.CommDestroy(ctxs[g]->comm); ctxs[g]->comm = nullptr; }
     NC(g_nccl.CommInitAll(comms.data(), count, devs.data()));
     for (int g = 0; g < count; ++g) ctxs[g]->comm = comms[g];
     return NBX_OK;
@@ -917,9 +1165,12 @@ int nbx_p2p_export(nbx_ctx *c, void *blob_out)
     b.pid = (int64_t)getpid();
     b.device = c->device;
     b.raw[0] = c->pos[0]; b.raw[1] = c->pos[1]; b.raw[2] = c->flags;
-    CU(cudaIpcGetMemHandle(&b.h[0], c->pos[0]));
-    CU(cudaIpcGetMemHandle(&b.h[1], c->pos[1]));
-    CU(cudaIpcGetMemHandle(&b.h[2], c->flags));
+    // IPC handles serve peers in OTHER processes; inside one process the raw pointers are used, so a
+    // platform without CUDA IPC can still run the one-process group
+    b.pad = 1;
+    void *bufs[3] = {c->pos[0], c->pos[1], c->flags};
+    for (int k = 0; k < 3; ++k)
+        if (cudaIpcGetMemHandle(&b.h[k], bufs[k]) != cudaSuccess) { cudaGetLastError(); b.pad = 0; }
     std::memset(blob_out, 0, NBX_P2P_BLOB_BYTES);
     std::memcpy(blob_out, &b, sizeof b);
     return NBX_OK;
@@ -939,7 +1190,9 @@ int nbx_p2p_attach(nbx_ctx *c, const void *blobs)
             continue;
         }
         void *ptr[3];
-        if (b.pid == (int64_t)getpid()) {
+        if (b.pid == (int64_t)getpid() && b.device == c->device) {
+            for (int k = 0; k < 3; ++k) ptr[k] = b.raw[k];        // two shards on one GPU: plain pointers
+        } else if (b.pid == (int64_t)getpid()) {
             int can = 0;
             CU(cudaDeviceCanAccessPeer(&can, c->device, b.device));
             if (!can) return fail(NBX_ERR_CUDA, "device %d cannot access peer %d", c->device, b.device);
@@ -949,6 +1202,7 @@ int nbx_p2p_attach(nbx_ctx *c, const void *blobs)
             cudaGetLastError();
             for (int k = 0; k < 3; ++k) ptr[k] = b.raw[k];
         } else {
+            if (!b.pad) return fail(NBX_ERR_CUDA, "rank %d could not export CUDA IPC handles", g);
             for (int k = 0; k < 3; ++k) {
                 CU(cudaIpcOpenMemHandle(&ptr[k], b.h[k], cudaIpcMemLazyEnablePeerAccess));
                 c->ipc_opened.push_back(ptr[k]);

@@ -43,7 +43,9 @@ struct StepParams {
     int *ke_ticket;         // [1]
     double *ke_out;         // [steps] kinetic energy, slot = *dev_step
     int *dev_step;          // step index inside the current run (reset by the host per run)
+    int ke_cap;             // slots in ke_out
     int *dev_epoch;         // steps completed since create (never reset; P2P flag value)
+    int *dev_err;           // device error word (0 = fine): peer timeout, host abort, debug-build check
     float4 *acc_out;        // non-null: store accelerations, do not update (nbx_accelerations)
     int n_pad;
     int i_begin, i_count;
@@ -62,7 +64,11 @@ struct StepParams {
     float4 *peer_pos_out[kMaxWorld];  // [g] = rank g's pos_out (self entry unused)
     int *peer_flags[kMaxWorld];       // [g] = rank g's flags[kMaxWorld]; we write slot [rank]
     const int *my_flags;              // this rank's flags[kMaxWorld]
+    unsigned long long peer_wait_ns;  // how long a step may wait for a peer's previous step
 };
+
+// Values of *dev_err (low byte; the rest carries detail: peer rank << 8, or source line << 8).
+enum { kDevErrPeerTimeout = 1, kDevErrHostAbort = 2, kDevErrDebugCheck = 3 };
 
 // ------------------------------------------------------------------------------
 //  PTX helpers: mbarrier + 1-D TMA bulk copy (SASS: SYNCS.*, UBLKCP)
@@ -125,6 +131,31 @@ __device__ __forceinline__ void st_release_sys(int *p, int v)
 {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ int ld_volatile(const int *p)
+{
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dev_fail(int *err, int code) { atomicCAS(err, 0, code); }
+
+// Debug build (make DEBUG=1 -> libnbx_debug.so): every index the kernel stores through and every
+// ticket value is range-checked; a failed check records its source line in *dev_err and nbx_run
+// returns NBX_ERR_DEBUG.  (compute-sanitizer is closed on the GPU pool this was developed on.)
+#ifdef NBX_DEBUG
+#define NBX_CHECK(cond)                                                                  \
+    do {                                                                                 \
+        if (!(cond)) nbx::dev_fail(p.dev_err, nbx::kDevErrDebugCheck | (__LINE__ << 8)); \
+    } while (0)
+#else
+#define NBX_CHECK(cond) ((void)0)
+#endif
 
 // Packed (FADD2/FMUL2/FFMA2) or scalar form of a two-lane FP32 op.
 template <bool SCALAR> __device__ __forceinline__ float2 add2(float2 a, float2 b)
@@ -210,18 +241,38 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid == 0) {
+        // A poisoned context (peer timeout, host abort, failed debug check) drains: every CTA of
+        // every queued step returns at once.
+#ifdef NBX_DEBUG
+        int bad = ld_volatile(p.dev_err);
+#else
+        int bad = p.p2p ? ld_volatile(p.dev_err) : 0;   // single-GPU runs never set it: skip the load
+#endif
         // P2P exchange: every rank must have finished the previous step (its epilogue wrote
         // into OUR pos_in) before we read it.  Peers run on other GPUs; no kernel on this
-        // GPU is waited on.
-        if (p.p2p) {
+        // GPU is waited on.  The wait is bounded: a dead or stuck peer turns into an error
+        // word that nbx_run reports as NBX_ERR_PEER instead of a hang.
+        if (p.p2p && !bad) {
             const int epoch = *p.dev_epoch;
-            for (int g = 0; g < p.world; ++g)
-                if (g != p.rank)
-                    while (ld_acquire_sys(&p.my_flags[g]) < epoch) { }
+            for (int g = 0; g < p.world && !bad; ++g) {
+                if (g == p.rank || ld_acquire_sys(&p.my_flags[g]) >= epoch) continue;
+                const unsigned long long t0 = globaltimer_ns();
+                while (ld_acquire_sys(&p.my_flags[g]) < epoch) {
+                    if ((bad = ld_volatile(p.dev_err)) != 0) break;
+                    if (globaltimer_ns() - t0 > p.peer_wait_ns) {
+                        dev_fail(p.dev_err, kDevErrPeerTimeout | (g << 8));
+                        bad = 1;
+                        break;
+                    }
+                    __nanosleep(200);
+                }
+            }
             asm volatile("fence.proxy.async;" ::: "memory");
         }
+        *s_flag = bad;
     }
     __syncthreads();
+    if (*s_flag) return;
 
     auto issue_tile = [&](int t) {
         const int cnt = min(TJ, je - (jb + t * TJ));
@@ -229,6 +280,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         if (j0 >= p.n_pad) j0 -= p.n_pad;
         const int head = min(cnt, p.n_pad - j0);
         const int st = t % STAGES;
+        NBX_CHECK(cnt > 0 && (cnt & 7) == 0 && j0 >= 0 && j0 + head <= p.n_pad && (j0 & 7) == 0);
         mbar_expect_tx(&full[st], (uint32_t)cnt * 16u);
         tma_load_1d(tiles + st * TJ, p.pos_in + j0, (uint32_t)head * 16u, &full[st]);
         if (head < cnt) tma_load_1d(tiles + st * TJ + head, p.pos_in, (uint32_t)(cnt - head) * 16u, &full[st]);
@@ -248,8 +300,11 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         int ip = pair_base + k * THREADS;
         ip = min(ip, (p.i_count >> 1) - 1);               // clamp: tail threads redo the last record
         const size_t gp = (size_t)(p.i_begin >> 1) + ip;
-        const float4 q0 = __ldg(&p.pos_in[2 * gp]);
-        const float4 q1 = __ldg(&p.pos_in[2 * gp + 1]);
+        // plain (L2) loads, not ld.global.nc: under programmatic dependent launch this kernel's
+        // lifetime overlaps the previous step's grid, which was still writing this buffer
+        NBX_CHECK(ip >= 0 && 2 * gp + 1 < (size_t)p.n_pad);
+        const float4 q0 = __ldcg(&p.pos_in[2 * gp]);
+        const float4 q1 = __ldcg(&p.pos_in[2 * gp + 1]);
         nx[2 * k] = make_float2(-q0.x, -q0.x); nx[2 * k + 1] = make_float2(-q0.y, -q0.y);
         ny[2 * k] = make_float2(-q0.z, -q0.z); ny[2 * k + 1] = make_float2(-q0.w, -q0.w);
         nz[2 * k] = make_float2(-q1.x, -q1.x); nz[2 * k + 1] = make_float2(-q1.y, -q1.y);
@@ -368,6 +423,8 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         for (int k = 0; k < R2; ++k) {
             const int ip = pair_base + k * THREADS;
             if (2 * ip < p.i_count) {
+                NBX_CHECK(p.part != nullptr && 2 * ip - tb0 >= 0 && 2 * ip + 1 - tb0 < p.split_bodies &&
+                          p.split_base + split < p.split_total);
                 mine[2 * ip] = make_float4(fx[2 * k], fy[2 * k], fz[2 * k], 0.f);
                 mine[2 * ip + 1] = make_float4(fx[2 * k + 1], fy[2 * k + 1], fz[2 * k + 1], 0.f);
             }
@@ -375,7 +432,11 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         __threadfence();
         __syncthreads();
         int *ticket = &p.tile_ticket[tile - p.whole_tiles];
-        if (tid == 0) *s_flag = (atomicAdd(ticket, 1) == contributors - 1);
+        if (tid == 0) {
+            const int arrived = atomicAdd(ticket, 1);
+            NBX_CHECK(arrived >= 0 && arrived < contributors && tile - p.whole_tiles < p.i_tiles - p.whole_tiles);
+            *s_flag = (arrived == contributors - 1);
+        }
         __syncthreads();
         if (!*s_flag) return;
         __threadfence();
@@ -404,6 +465,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     for (int k = 0; k < R2; ++k) {
         const int ip = pair_base + k * THREADS;
         if (2 * ip >= p.i_count) continue;
+        NBX_CHECK(ip >= 0 && 2 * ip + 1 < p.i_count);
         if (p.acc_out != nullptr) {
             p.acc_out[2 * ip] = make_float4(fx[2 * k], fy[2 * k], fz[2 * k], 0.f);
             p.acc_out[2 * ip + 1] = make_float4(fx[2 * k + 1], fy[2 * k + 1], fz[2 * k + 1], 0.f);
@@ -418,12 +480,14 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                                       fmaf(v0.y, p.dt, -ny[2 * k].x), fmaf(v1.y, p.dt, -ny[2 * k + 1].x));
         const float2 r1 = make_float2(fmaf(v0.z, p.dt, -nz[2 * k].x), fmaf(v1.z, p.dt, -nz[2 * k + 1].x));
         const size_t gp = (size_t)(p.i_begin >> 1) + ip;
+        NBX_CHECK(2 * gp + 1 < (size_t)p.n_pad);
         p.pos_out[2 * gp] = r0;
         *reinterpret_cast<float2 *>(&p.pos_out[2 * gp + 1]) = r1;      // Gm0,Gm1 never change
         if (p.p2p) {
             for (int g = 0; g < p.world; ++g) {
                 if (g == p.rank) continue;
                 float4 *dst = p.peer_pos_out[g];
+                NBX_CHECK(dst != nullptr && dst != p.pos_out);
                 dst[2 * gp] = r0;                                       // NVLink store
                 *reinterpret_cast<float2 *>(&dst[2 * gp + 1]) = r1;
             }
@@ -442,9 +506,12 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     if (tid == 0) {
         double s = 0.0;
         for (int w = 0; w < WARPS; ++w) s += red[w];
+        NBX_CHECK(tile >= 0 && tile < p.i_tiles);
         p.ke_part[tile] = s;
         __threadfence();
-        *s_flag = (atomicAdd(p.ke_ticket, 1) == p.i_tiles - 1);
+        const int arrived = atomicAdd(p.ke_ticket, 1);
+        NBX_CHECK(arrived >= 0 && arrived < p.i_tiles);
+        *s_flag = (arrived == p.i_tiles - 1);
     }
     __syncthreads();
     if (!*s_flag) return;
@@ -460,6 +527,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         double tot = 0.0;
         for (int w = 0; w < WARPS; ++w) tot += red[w];
         const int step = *p.dev_step;
+        NBX_CHECK(step >= 0 && step < p.ke_cap);
         p.ke_out[step] = 0.5 * tot;
         *p.dev_step = step + 1;
         *p.ke_ticket = 0;
@@ -476,30 +544,34 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
 // ------------------------------------------------------------------------------
 //  Layout kernels: host SoA staging <-> pair-packed records.
 // ------------------------------------------------------------------------------
-// stage = 7 arrays of n floats: px py pz vx vy vz mass.  Bodies >= n are zero-mass padding.
-__global__ void pack_kernel(const float *__restrict__ stage, int n, int n_pad, int i_begin, int i_count,
-                            float G, float4 *__restrict__ pos_a, float4 *__restrict__ pos_b,
-                            float4 *__restrict__ vel)
+// stage = 7 arrays of `stride` floats (px py pz vx vy vz mass) holding bodies [first, first + stride)
+// of the caller's arrays.  Packs records [rec_begin, rec_begin + rec_count); bodies >= n are
+// zero-mass padding.  pos_b may be null (sharded upload: the second replica is copied afterwards).
+__global__ void pack_kernel(const float *__restrict__ stage, int stride, int first, int n, int rec_begin,
+                            int rec_count, int i_begin, int i_count, float G, float4 *__restrict__ pos_a,
+                            float4 *__restrict__ pos_b, float4 *__restrict__ vel)
 {
-    const int rec = blockIdx.x * blockDim.x + threadIdx.x;   // record = body pair
-    if (2 * rec >= n_pad) return;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rec_count) return;
+    const int rec = rec_begin + r;                           // record = body pair
     float x[2], y[2], z[2], m[2], vx[2], vy[2], vz[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int i = 2 * rec + h;
-        const bool live = i < n;
-        x[h] = live ? stage[i] : 0.f;
-        y[h] = live ? stage[(size_t)n + i] : 0.f;
-        z[h] = live ? stage[2 * (size_t)n + i] : 0.f;
-        vx[h] = live ? stage[3 * (size_t)n + i] : 0.f;
-        vy[h] = live ? stage[4 * (size_t)n + i] : 0.f;
-        vz[h] = live ? stage[5 * (size_t)n + i] : 0.f;
-        m[h] = live ? stage[6 * (size_t)n + i] : 0.f;
+        const int k = i - first;
+        const bool live = i < n && k >= 0 && k < stride;
+        x[h] = live ? stage[k] : 0.f;
+        y[h] = live ? stage[(size_t)stride + k] : 0.f;
+        z[h] = live ? stage[2 * (size_t)stride + k] : 0.f;
+        vx[h] = live ? stage[3 * (size_t)stride + k] : 0.f;
+        vy[h] = live ? stage[4 * (size_t)stride + k] : 0.f;
+        vz[h] = live ? stage[5 * (size_t)stride + k] : 0.f;
+        m[h] = live ? stage[6 * (size_t)stride + k] : 0.f;
     }
     const float4 q0 = make_float4(x[0], x[1], y[0], y[1]);
     const float4 q1 = make_float4(z[0], z[1], G * m[0], G * m[1]);
     pos_a[2 * rec] = q0; pos_a[2 * rec + 1] = q1;
-    pos_b[2 * rec] = q0; pos_b[2 * rec + 1] = q1;
+    if (pos_b != nullptr) { pos_b[2 * rec] = q0; pos_b[2 * rec + 1] = q1; }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int li = 2 * rec + h - i_begin;
@@ -507,24 +579,37 @@ __global__ void pack_kernel(const float *__restrict__ stage, int n, int n_pad, i
     }
 }
 
-// stage = 6 arrays of n floats: px py pz (all bodies) vx vy vz (this shard's range only).
-__global__ void unpack_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ vel, int n,
-                              int i_begin, int i_count, float *__restrict__ stage)
+// stage = 6 arrays of `stride` floats: px py pz vx vy vz of bodies [first, first + count), count <=
+// stride; velocities are written only for bodies of this shard ([i_begin, i_begin + i_count)).
+__global__ void unpack_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ vel, int stride, int first,
+                              int count, int i_begin, int i_count, float *__restrict__ stage)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int i = first + k;
     const float *rec = reinterpret_cast<const float *>(pos + 2 * (size_t)(i >> 1));
     const int h = i & 1;
-    stage[i] = rec[h];
-    stage[(size_t)n + i] = rec[2 + h];
-    stage[2 * (size_t)n + i] = rec[4 + h];
+    stage[k] = rec[h];
+    stage[(size_t)stride + k] = rec[2 + h];
+    stage[2 * (size_t)stride + k] = rec[4 + h];
     const int li = i - i_begin;
     if (li >= 0 && li < i_count) {
         const float4 v = vel[li];
-        stage[3 * (size_t)n + i] = v.x;
-        stage[4 * (size_t)n + i] = v.y;
-        stage[5 * (size_t)n + i] = v.z;
+        stage[3 * (size_t)stride + k] = v.x;
+        stage[4 * (size_t)stride + k] = v.y;
+        stage[5 * (size_t)stride + k] = v.z;
     }
+}
+
+// float4 accelerations of a shard -> 3 SoA arrays of `count` floats (nbx_accelerations).
+__global__ void acc_soa_kernel(const float4 *__restrict__ acc, int count, float *__restrict__ stage)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const float4 a = acc[k];
+    stage[k] = a.x;
+    stage[(size_t)count + k] = a.y;
+    stage[2 * (size_t)count + k] = a.z;
 }
 
 }  // namespace nbx

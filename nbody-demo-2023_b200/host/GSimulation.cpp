@@ -8,7 +8,8 @@
 //
 // Environment (all optional; none changes `./nbody.x N S` output):
 //   NBODY_GPUS=G        shard the i-bodies over G GPUs of this node (default 1)
-//   NBODY_EXCHANGE=nccl|nccl_overlap|p2p   multi-GPU position exchange (default nccl)
+//   NBODY_EXCHANGE=p2p|nccl|nccl_overlap   multi-GPU position exchange (default p2p = the library default;
+//                       falls back to nccl when the GPUs cannot map each other's memory)
 //   NBODY_SFREQ=k       print a row every k steps (default 50, ver0:31)
 //   NBODY_IC=uniform|plummer  initial positions (default: the reference's uniform cube)
 //   NBODY_DUMP=file     write the final state (NBXD format, see oracle/ref_harness.cpp)
@@ -47,16 +48,12 @@ int env_int(const char *name, int dflt)
 
 bool GSimulation::s_banner = true;
 
-GSimulation::GSimulation() : particles(nullptr), _kenergy(0), _totTime(0), _totFlops(0), _ngpus(1), _ic("uniform")
+GSimulation::GSimulation()
 {
     if (s_banner) {
         std::cout << "===============================" << std::endl;
         std::cout << " Initialize Gravity Simulation" << std::endl;
     }
-    set_npart(2000);
-    set_nsteps(500);
-    set_tstep(0.1);
-    set_sfreq(50);
     _ngpus = env_int("NBODY_GPUS", 1);
     set_sample_frequency(env_int("NBODY_SFREQ", 0));
     if (const char *ic = std::getenv("NBODY_IC")) _ic = ic;
@@ -65,31 +62,31 @@ GSimulation::GSimulation() : particles(nullptr), _kenergy(0), _totTime(0), _totF
 GSimulation::~GSimulation() { delete particles; }
 
 void GSimulation::init() {}
-void GSimulation::set_number_of_particles(int N) { set_npart(N); }
-void GSimulation::set_number_of_steps(int N) { set_nsteps(N); }
+void GSimulation::set_number_of_particles(int N) { cfg.npart = N; }
+void GSimulation::set_number_of_steps(int N) { cfg.nsteps = N; }
 
 // ver0/GSimulation.cpp:44-93: each of the three re-seeds its own mt19937 with 42.
 void GSimulation::init_pos()
 {
     ParticleSoA &p = *particles;
     if (_ic == "plummer")
-        nbx_ic::plummer_pos(get_npart(), p.pos_x.data(), p.pos_y.data(), p.pos_z.data());
+        nbx_ic::plummer_pos(cfg.npart, p.pos_x.data(), p.pos_y.data(), p.pos_z.data());
     else
-        nbx_ic::uniform_pos(get_npart(), p.pos_x.data(), p.pos_y.data(), p.pos_z.data());
+        nbx_ic::uniform_pos(cfg.npart, p.pos_x.data(), p.pos_y.data(), p.pos_z.data());
 }
 void GSimulation::init_vel()
 {
     ParticleSoA &p = *particles;
-    nbx_ic::uniform_vel(get_npart(), p.vel_x.data(), p.vel_y.data(), p.vel_z.data());
+    nbx_ic::uniform_vel(cfg.npart, p.vel_x.data(), p.vel_y.data(), p.vel_z.data());
 }
 void GSimulation::init_acc() {}   // accelerations exist only in the kernel's registers
-void GSimulation::init_mass() { nbx_ic::uniform_mass(get_npart(), particles->mass.data()); }
+void GSimulation::init_mass() { nbx_ic::uniform_mass(cfg.npart, particles->mass.data()); }
 
 void GSimulation::start()
 {
-    const int n = get_npart();
-    const int nsteps = get_nsteps();
-    const int sfreq = get_sfreq();
+    const int n = cfg.npart;
+    const int nsteps = cfg.nsteps;
+    const int sfreq = cfg.sfreq;
     if (n < 1) { std::cerr << "nbody.x: nPart must be >= 1" << std::endl; std::exit(1); }
 
     particles = new ParticleSoA;
@@ -138,31 +135,39 @@ void GSimulation::start()
     const float Gconst = 6.67259e-11f;      // ver2/GSimulation.cpp:116
     std::vector<nbx_ctx *> ctx((size_t)G, nullptr);
     const char *xch = std::getenv("NBODY_EXCHANGE");
-    const long long exchange = (xch && std::strcmp(xch, "p2p") == 0) ? NBX_EXCHANGE_P2P
-                               : (xch && std::strcmp(xch, "nccl_overlap") == 0) ? NBX_EXCHANGE_NCCL_OVERLAP : NBX_EXCHANGE_NCCL;
+    long long exchange = (xch && std::strcmp(xch, "nccl") == 0) ? NBX_EXCHANGE_NCCL
+                         : (xch && std::strcmp(xch, "nccl_overlap") == 0) ? NBX_EXCHANGE_NCCL_OVERLAP : NBX_EXCHANGE_P2P;
+    // NCCL_DEBUG=VERSION/INFO makes NCCL print to stdout, between the banner and the table: keep
+    // stdout byte-compatible with the reference by sending NCCL's log to stderr unless told otherwise
+    if (G > 1) setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     for (int g = 0; g < G; ++g) {
-        if (nbx_create(&ctx[g], n, g, g, G, get_tstep(), Gconst, softeningSquared)) die("nbx_create");
+        if (nbx_create(&ctx[g], n, g, g, G, cfg.tstep, Gconst, softeningSquared)) die("nbx_create");
         if (forced_variant >= 0 && nbx_set_option(ctx[g], "variant", forced_variant)) die("variant");
         if (std::getenv("NBODY_VARIANT") && nbx_set_option(ctx[g], "variant", env_int("NBODY_VARIANT", 0))) die("variant");
         if (std::getenv("NBODY_JSPLITS") && nbx_set_option(ctx[g], "j_splits", env_int("NBODY_JSPLITS", 0))) die("j_splits");
         if (std::getenv("NBODY_GRAPH") && nbx_set_option(ctx[g], "graph", env_int("NBODY_GRAPH", -1))) die("graph");
         if (std::getenv("NBODY_ACCURATE") && nbx_set_option(ctx[g], "accurate", env_int("NBODY_ACCURATE", 0))) die("accurate");
-        if (nbx_set_option(ctx[g], "exchange", exchange)) die("exchange");
-        if (nbx_upload(ctx[g], particles->pos_x.data(), particles->pos_y.data(), particles->pos_z.data(),
-                       particles->vel_x.data(), particles->vel_y.data(), particles->vel_z.data(),
-                       particles->mass.data()))
-            die("nbx_upload");
+        if (std::getenv("NBODY_PEER_TIMEOUT_MS") && nbx_set_option(ctx[g], "peer_timeout_ms", env_int("NBODY_PEER_TIMEOUT_MS", 30000))) die("peer_timeout_ms");
     }
-    if (G > 1) {
-        if (nbx_comm_init_all(ctx.data(), G)) die("nbx_comm_init_all");
-        if (exchange == NBX_EXCHANGE_P2P) {
-            std::vector<unsigned char> blobs((size_t)G * NBX_P2P_BLOB_BYTES);
-            for (int g = 0; g < G; ++g)
-                if (nbx_p2p_export(ctx[g], blobs.data() + (size_t)g * NBX_P2P_BLOB_BYTES)) die("nbx_p2p_export");
-            for (int g = 0; g < G; ++g)
-                if (nbx_p2p_attach(ctx[g], blobs.data())) die("nbx_p2p_attach");
+    if (G > 1 && exchange == NBX_EXCHANGE_P2P) {
+        // map every GPU's replica into every other GPU; if some pair has no peer access, take the
+        // NCCL all-gather on all GPUs instead (both are GPU paths)
+        std::vector<unsigned char> blobs((size_t)G * NBX_P2P_BLOB_BYTES);
+        bool ok = true;
+        for (int g = 0; g < G && ok; ++g) ok = nbx_p2p_export(ctx[g], blobs.data() + (size_t)g * NBX_P2P_BLOB_BYTES) == NBX_OK;
+        for (int g = 0; g < G && ok; ++g) ok = nbx_p2p_attach(ctx[g], blobs.data()) == NBX_OK;
+        if (!ok) {
+            std::cerr << "nbody.x: P2P exchange unavailable (" << nbx_last_error() << "); using the NCCL all-gather" << std::endl;
+            exchange = NBX_EXCHANGE_NCCL;
         }
     }
+    for (int g = 0; g < G; ++g)
+        if (nbx_set_option(ctx[g], "exchange", exchange)) die("exchange");
+    if (G > 1 && exchange != NBX_EXCHANGE_P2P && nbx_comm_init_all(ctx.data(), G)) die("nbx_comm_init_all");
+    // each GPU takes its own shard over PCIe; the packed records go GPU to GPU
+    if (nbx_upload_group(ctx.data(), G, particles->pos_x.data(), particles->pos_y.data(), particles->pos_z.data(),
+                         particles->vel_x.data(), particles->vel_y.data(), particles->vel_z.data(), particles->mass.data()))
+        die("nbx_upload");
 
     print_header();
 
@@ -189,7 +194,7 @@ void GSimulation::start()
             nf += 1;
             std::cout << " "
                       << std::left << std::setw(8) << s
-                      << std::left << std::setprecision(5) << std::setw(8) << s * get_tstep()
+                      << std::left << std::setprecision(5) << std::setw(8) << s * cfg.tstep
                       << std::left << std::setprecision(5) << std::setw(12) << _kenergy
                       << std::left << std::setprecision(5) << std::setw(12) << (ts1 - ts0)
                       << std::left << std::setprecision(5) << std::setw(12) << gflops * sfreq / (ts1 - ts0)
@@ -255,9 +260,9 @@ void GSimulation::start()
 
 void GSimulation::print_header()
 {
-    std::cout << " nPart = " << get_npart() << "; "
-              << "nSteps = " << get_nsteps() << "; "
-              << "dt = " << get_tstep() << std::endl;
+    std::cout << " nPart = " << cfg.npart << "; "
+              << "nSteps = " << cfg.nsteps << "; "
+              << "dt = " << cfg.tstep << std::endl;
     std::cout << "------------------------------------------------" << std::endl;
     std::cout << " "
               << std::left << std::setw(8) << "s"

@@ -37,21 +37,23 @@ public:
 
     // extensions (not in the reference; defaults keep `./nbody.x N S` identical)
     void set_number_of_gpus(int G) { _ngpus = G; }
-    void set_sample_frequency(int sf) { if (sf > 0) _sfreq = sf; }
+    void set_sample_frequency(int sf) { if (sf > 0) cfg.sfreq = sf; }
     real_type kenergy() const { return _kenergy; }
 
 private:
-    ParticleSoA *particles;
-
-    int _npart;        // number of particles
-    int _nsteps;       // number of integration steps
-    real_type _tstep;  // time step of the simulation
-    int _sfreq;        // sample frequency
-    real_type _kenergy;  // kinetic energy
-    double _totTime;   // total time of the simulation
-    double _totFlops;  // total number of flops
-    int _ngpus;
-    std::string _ic;   // "uniform" (reference) or "plummer"
+    // State of one run.  (The reference keeps the same quantities -- verN/GSimulation.hpp:48-59 --
+    // behind per-field inline accessors; only the five public calls above are its interface.)
+    struct Config {
+        int npart = 2000;          // ver0/GSimulation.cpp:28
+        int nsteps = 500;          // :29
+        real_type tstep = 0.1f;    // :30
+        int sfreq = 50;            // :31, rows every sfreq steps
+    } cfg;
+    ParticleSoA *particles = nullptr;
+    real_type _kenergy = 0;
+    double _totTime = 0, _totFlops = 0;
+    int _ngpus = 1;
+    std::string _ic = "uniform";   // or "plummer"
     int _devices = 0, _thread_dim0 = 0, _thread_dim1 = 0;
     float _cpu_ratio = -1.0f;
     static bool s_banner;
@@ -60,16 +62,6 @@ private:
     void init_vel();
     void init_acc();
     void init_mass();
-
-    inline void set_npart(const int &N) { _npart = N; }
-    inline int get_npart() const { return _npart; }
-    inline void set_tstep(const real_type &dt) { _tstep = dt; }
-    inline real_type get_tstep() const { return _tstep; }
-    inline void set_nsteps(const int &n) { _nsteps = n; }
-    inline int get_nsteps() const { return _nsteps; }
-    inline void set_sfreq(const int &sf) { _sfreq = sf; }
-    inline int get_sfreq() const { return _sfreq; }
-
     void print_header();
 };
 

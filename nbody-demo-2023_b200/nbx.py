@@ -12,8 +12,13 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnbx.so")
+# NBX_LIB selects another build of the same ABI (the bounds-checked libnbx_debug.so, the tuning
+# tools' libnbx_ablation.so); a bare file name is looked up next to this file.
+LIB_PATH = os.environ.get("NBX_LIB") or os.path.join(_HERE, "libnbx.so")
+if not os.path.isabs(LIB_PATH) and not os.path.exists(LIB_PATH):
+    LIB_PATH = os.path.join(_HERE, LIB_PATH)
 
+ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_STATE, ERR_NODEVICE, ERR_PEER, ERR_DEBUG = 1, 2, 3, 4, 5, 6, 7
 EXCHANGE_NCCL = 0
 EXCHANGE_P2P = 1
 EXCHANGE_NCCL_OVERLAP = 2
@@ -24,7 +29,7 @@ P2P_BLOB_BYTES = 256
 SYMBOLS = [
     "nbx_abi_version", "nbx_last_error", "nbx_device_count", "nbx_create", "nbx_destroy",
     "nbx_set_option", "nbx_get_info", "nbx_plan", "nbx_variant_count", "nbx_variant_name", "nbx_upload",
-    "nbx_download", "nbx_run", "nbx_accelerations", "nbx_simulate", "nbx_comm_unique_id",
+    "nbx_download", "nbx_upload_sharded", "nbx_upload_group", "nbx_download_shard", "nbx_run", "nbx_accelerations", "nbx_simulate", "nbx_comm_unique_id",
     "nbx_comm_init", "nbx_comm_init_all", "nbx_run_group", "nbx_p2p_export", "nbx_p2p_attach",
     "nbx_ic_uniform", "nbx_ic_plummer", "nbx_gflop_per_step", "nbx_host_alloc", "nbx_host_free",
 ]
@@ -42,7 +47,8 @@ class Info(C.Structure):
         "i_begin", "i_count", "threads", "bodies_per_thread", "tile_bodies", "stages",
         "i_tiles", "whole_tiles", "j_splits", "ctas_per_sm", "use_graph", "exchange", "variant")] + [
         ("kernel_launches", C.c_longlong), ("aux_launches", C.c_longlong),
-        ("last_run_seconds", C.c_double), ("kernel_seconds_total", C.c_double)]
+        ("last_run_seconds", C.c_double), ("kernel_seconds_total", C.c_double),
+        ("device_error", C.c_int), ("peer_timeout_ms", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -75,6 +81,9 @@ def lib() -> C.CDLL:
         L.nbx_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.POINTER(Info)]
         L.nbx_upload.argtypes = [C.c_void_p] + [_f32p] * 7
         L.nbx_download.argtypes = [C.c_void_p] + [_f32p] * 6
+        L.nbx_upload_sharded.argtypes = [C.c_void_p] + [_f32p] * 7
+        L.nbx_upload_group.argtypes = [C.POINTER(C.c_void_p), C.c_int] + [_f32p] * 7
+        L.nbx_download_shard.argtypes = [C.c_void_p] + [_f32p] * 6
         L.nbx_run.argtypes = [C.c_void_p, C.c_int, _f64p, _f64p]
         L.nbx_accelerations.argtypes = [C.c_void_p] + [_f32p] * 3
         L.nbx_simulate.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float] + [_f32p] * 7 + [_f64p, _f64p]
@@ -180,6 +189,14 @@ class Context:
     def download(self, px, py, pz, vx, vy, vz):
         _check(lib().nbx_download(self._h, *[_p(a) for a in (px, py, pz, vx, vy, vz)]))
 
+    def upload_sharded(self, px, py, pz, vx, vy, vz, mass):
+        """Collective: each rank copies only its own shard over PCIe; NCCL all-gathers the packed records."""
+        _check(lib().nbx_upload_sharded(self._h, *[_p(a) for a in (px, py, pz, vx, vy, vz, mass)]))
+
+    def download_shard(self, px, py, pz, vx, vy, vz):
+        """Writes only this context's [i_begin, i_begin+i_count) of the six arrays."""
+        _check(lib().nbx_download_shard(self._h, *[_p(a) for a in (px, py, pz, vx, vy, vz)]))
+
     def state(self):
         arrs = [np.zeros(self.n, dtype=np.float32) for _ in range(6)]
         self.download(*arrs)
@@ -223,6 +240,11 @@ def comm_unique_id() -> bytes:
 def comm_init_all(ctxs):
     arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
     _check(lib().nbx_comm_init_all(arr, len(ctxs)))
+
+
+def upload_group(ctxs, px, py, pz, vx, vy, vz, mass):
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    _check(lib().nbx_upload_group(arr, len(ctxs), *[_p(a) for a in (px, py, pz, vx, vy, vz, mass)]))
 
 
 def run_group(ctxs, nsteps: int):

@@ -164,6 +164,35 @@ def ref_run(ver: str, n: int, nsteps: int, threads: int | None = None):
     return s, ke, secs
 
 
+def write_dump(path: str, state: "State", steps: int = 0, ke: float = 0.0, secs: float = 0.0) -> None:
+    """Write `state` in the NBXD layout (what NBODY_DUMP / ref_dump_verN / ref_state_verN exchange)."""
+    with open(path, "wb") as f:
+        f.write(b"NBXD" + struct.pack("<iifd", state.n, steps, ke, secs))
+        for fld in State.FIELDS:
+            f.write(np.ascontiguousarray(getattr(state, fld), dtype=np.float32).tobytes())
+
+
+def ref_state_available(ver: str = "ver8") -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "ref_state_" + ver))
+
+
+def ref_state_run(ver: str, state: "State", nsteps: int, threads: int | None = None):
+    """Run the compiled reference `ver` for nsteps FROM `state` (any initial conditions, e.g. Plummer)
+    through ref_state_verN; returns (State after nsteps, kenergy float32[nsteps], loop_seconds)."""
+    exe = os.path.join(REF_DIR, "ref_state_" + ver)
+    env = dict(os.environ)
+    if threads is not None:
+        env["OMP_NUM_THREADS"] = str(threads)
+    env.setdefault("OMP_PROC_BIND", "close")
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout, fke = (os.path.join(td, x) for x in ("in.nbxd", "out.nbxd", "ke.txt"))
+        write_dump(fin, state)
+        subprocess.run([exe, fin, str(nsteps), fout, fke], check=True, env=env)
+        s, _, secs, _ = read_dump(fout)
+        ke = np.loadtxt(fke, dtype=np.float64, ndmin=1).astype(np.float32) if nsteps > 0 else np.zeros(0, np.float32)
+    return s, ke, secs
+
+
 def ref_cuda_available() -> bool:
     return os.path.exists(os.path.join(REF_DIR, "ver5_all_cuda", "nbody.x"))
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(pkg, nbx):
     L = ctypes.CDLL(pkg.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.nbx_abi_version() == 1
+    assert L.nbx_abi_version() == 2
 
 
 def test_every_entry_point_cites_the_reference(pkg):
