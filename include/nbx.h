@@ -109,6 +109,7 @@ NBX_API void nbx_destroy(nbx_ctx *ctx);
  *   "graph"     1/0 replay steps from a CUDA graph (auto: on for small N)
  *   "accurate"  1/0 two-level accumulation (float per j tile, then double): large-N accuracy option
  *   "pdl"       1/0 programmatic dependent launch between consecutive steps (-1 = auto: many-wave grids only)
+ *   "smem_pad_kb"  extra dynamic shared memory per CTA in KiB (tuning: caps the resident CTAs per SM)
  *   "exchange"  NBX_EXCHANGE_* (default NBX_EXCHANGE_P2P)
  *   "peer_timeout_ms"  P2P exchange: how long a step may wait inside the kernel for a peer GPU to
  *               finish the previous step before the run fails with NBX_ERR_PEER (default 30000)
@@ -120,6 +121,11 @@ NBX_API int nbx_get_info(const nbx_ctx *ctx, nbx_info *out);
  * (host arithmetic only; fills the planning fields of nbx_info).  variant/j_splits: -1/0 = auto. */
 NBX_API int nbx_plan(int n, int rank, int world, int sm_count, int exchange, long long variant,
                      long long j_splits, nbx_info *out);
+/* Trace build only (make trace -> libnbx_trace.so; the product library returns NBX_ERR_STATE): per-CTA
+ * %globaltimer stamps of the first "trace_steps" (option) steps of the last run, 6 words per CTA per step:
+ * start, first j tile landed, j sweep done, exit, SM id, 1 if this CTA ran the split-combine + update.
+ * tools/trace_steps.py turns them into the launch-gap / prologue / sweep / combine split of a step. */
+NBX_API int nbx_trace_read(nbx_ctx *ctx, unsigned long long *out, size_t capacity_words, int *steps, int *ctas);
 NBX_API int nbx_variant_count(void);
 NBX_API const char *nbx_variant_name(int idx);
 

@@ -140,6 +140,10 @@ static const std::vector<Variant> &variants()
         make_variant<2, 256, 256, 4, 2, 2, 15>("r4_t256_u2_scalar"),  // no packed FP32 at all
         make_variant<2, 256, 256, 4, 2, 3, 16>("r4_t256_u2_stage_occ3"),   // 3 CTAs/SM x 85 registers
         make_variant<2, 256, 256, 4, 1, 3, 16>("r4_t256_u1_stage_occ3"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 128>("r4_t256_u4_stage_xjacc"),   // accumulate sum s*r_j, sum s (13 ops/pair)
+        make_variant<2, 256, 256, 4, 2, 2, 16 | 128>("r4_t256_u2_stage_xjacc"),
+        make_variant<2, 256, 256, 8, 4, 2, 16>("r4_t256_u4_stage_s8"),            // deeper TMA ring
+        make_variant<2, 256, 512, 4, 4, 2, 16>("r4_t256_u4_stage_tj512"),         // larger TMA tiles
 #endif
     };
     return v;
@@ -179,6 +183,9 @@ struct nbx_ctx {
     int peer_timeout_ms = 30000;
     int device_error = 0;              // last value read from counters[3]; non-zero = poisoned
     bool debug_fault = false;          // debug build only
+    int smem_pad = 0;                  // tuning knob ("smem_pad_kb")
+    unsigned long long *trace = nullptr;   // trace build only
+    int trace_steps = 0, trace_ctas = 0;
     bool resolved = false;
     int i_tiles = 0, whole_tiles = 0, j_splits = 1, split_bodies = 0, ctas_per_sm = 0, use_graph = 0;
 
@@ -287,9 +294,9 @@ static int resolve(nbx_ctx *c)
     const int splits = pl.j_splits;
     const Variant &v = variants()[c->variant];
     CU(cudaSetDevice(c->device));
-    CU(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
+    CU(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem + c->smem_pad));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, v.threads, v.smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, v.threads, v.smem + c->smem_pad));
     if (occ < 1) return fail(NBX_ERR_CUDA, "kernel variant %s cannot be resident", v.name);
     c->ctas_per_sm = occ;
 
@@ -302,6 +309,13 @@ static int resolve(nbx_ctx *c)
     CU(cudaMalloc(&c->ke_part, (size_t)c->i_tiles * sizeof(double)));
     if (c->graph2) { cudaGraphExecDestroy(c->graph2); c->graph2 = nullptr; }
     if (c->graph16) { cudaGraphExecDestroy(c->graph16); c->graph16 = nullptr; }
+    if (c->trace) { CU(cudaFree(c->trace)); c->trace = nullptr; }
+    c->trace_ctas = c->whole_tiles + (c->i_tiles - c->whole_tiles) * c->j_splits;
+    if (c->trace_steps > 0) {
+        const size_t bytes = (size_t)c->trace_steps * c->trace_ctas * nbx::kTraceWords * sizeof(unsigned long long);
+        CU(cudaMalloc(&c->trace, bytes));
+        CU(cudaMemset(c->trace, 0, bytes));
+    }
     c->resolved = true;
     return NBX_OK;
 }
@@ -324,6 +338,8 @@ static void fill_params(const nbx_ctx *c, StepParams &p, int in_buf, float4 *acc
     p.ke_out = c->ke_dev;
     p.ke_cap = c->debug_fault ? 0 : c->ke_cap;
     p.peer_wait_ns = (unsigned long long)c->peer_timeout_ms * 1000000ull;
+    p.trace = c->trace;
+    p.trace_steps = c->trace_steps;
     p.acc_out = acc_out;
     p.n_pad = c->n_pad;
     p.i_begin = c->i_begin;
@@ -370,7 +386,7 @@ static int launch_step(nbx_ctx *c, int in_buf, float4 *acc_out = nullptr, int ph
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
     cfg.blockDim = dim3(v.threads);
-    cfg.dynamicSmemBytes = v.smem;
+    cfg.dynamicSmemBytes = v.smem + c->smem_pad;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap our prologue with
@@ -627,7 +643,7 @@ void nbx_destroy(nbx_ctx *c)
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     cudaFree(c->pos[0]); cudaFree(c->pos[1]); cudaFree(c->vel); cudaFree(c->part); cudaFree(c->acc);
     cudaFree(c->tile_ticket); cudaFree(c->ke_part); cudaFree(c->counters); cudaFree(c->flags);
-    cudaFree(c->ke_dev); cudaFree(c->stage);
+    cudaFree(c->ke_dev); cudaFree(c->stage); cudaFree(c->trace);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_step) cudaEventDestroy(c->ev_step);
@@ -655,6 +671,14 @@ int nbx_set_option(nbx_ctx *c, const char *key, long long value)
         if (value != NBX_EXCHANGE_NCCL && value != NBX_EXCHANGE_P2P && value != NBX_EXCHANGE_NCCL_OVERLAP)
             return fail(NBX_ERR_ARG, "unknown exchange %lld", value);
         c->exchange = (int)value;
+#ifdef NBX_TRACE
+    } else if (k == "trace_steps") {   // record per-CTA timestamps of the first `value` steps of each run
+        if (value < 0 || value > 4096) return fail(NBX_ERR_ARG, "trace_steps out of range");
+        c->trace_steps = (int)value;
+#endif
+    } else if (k == "smem_pad_kb") {   // extra dynamic shared memory per CTA: lowers the resident CTAs per SM
+        if (value < 0 || value > 200) return fail(NBX_ERR_ARG, "smem_pad_kb out of range");
+        c->smem_pad = (int)value * 1024;
     } else if (k == "peer_timeout_ms") {
         if (value < 1 || value > 3600000) return fail(NBX_ERR_ARG, "peer_timeout_ms out of range");
         c->peer_timeout_ms = (int)value;
@@ -1097,6 +1121,23 @@ int nbx_simulate(int n, int nsteps, float dt, float G, float eps2,
             rc = nbx_download(c, px, py, pz, vx, vy, vz);
     nbx_destroy(c);
     return rc;
+}
+
+int nbx_trace_read(nbx_ctx *c, unsigned long long *out, size_t capacity_words, int *steps, int *ctas)
+{
+    if (!c || !steps || !ctas) return fail(NBX_ERR_ARG, "NULL argument");
+#ifndef NBX_TRACE
+    (void)out; (void)capacity_words;
+    return fail(NBX_ERR_STATE, "this library was built without -DNBX_TRACE (make trace -> libnbx_trace.so)");
+#else
+    *steps = c->trace_steps; *ctas = c->trace_ctas;
+    const size_t words = (size_t)c->trace_steps * c->trace_ctas * nbx::kTraceWords;
+    if (!c->trace || words == 0) return fail(NBX_ERR_STATE, "no trace recorded: set option trace_steps before the run");
+    if (!out || capacity_words < words) return fail(NBX_ERR_ARG, "trace needs %zu words", words);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpy(out, c->trace, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return NBX_OK;
+#endif
 }
 
 // ---- multi-GPU plumbing --------------------------------------------------------

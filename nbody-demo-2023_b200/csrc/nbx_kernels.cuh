@@ -65,7 +65,11 @@ struct StepParams {
     int *peer_flags[kMaxWorld];       // [g] = rank g's flags[kMaxWorld]; we write slot [rank]
     const int *my_flags;              // this rank's flags[kMaxWorld]
     unsigned long long peer_wait_ns;  // how long a step may wait for a peer's previous step
+    // Trace build (-DNBX_TRACE, libnbx_trace.so) only: per-CTA %globaltimer stamps, kTraceWords per CTA per step
+    unsigned long long *trace;
+    int trace_steps;                  // steps the buffer holds (later steps are not recorded)
 };
+constexpr int kTraceWords = 6;        // start, first tile landed, sweep done, exit, smid, last-arriver flag
 
 // Values of *dev_err (low byte; the rest carries detail: peer rank << 8, or source line << 8).
 enum { kDevErrPeerTimeout = 1, kDevErrHostAbort = 2, kDevErrDebugCheck = 3 };
@@ -212,6 +216,23 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     double *hi = reinterpret_cast<double *>(smem_raw + step_smem_bytes<THREADS, TJ, STAGES>());
 
     const int tid = threadIdx.x;
+#ifdef NBX_TRACE
+    unsigned long long *tr = nullptr;
+    if (tid == 0 && p.trace != nullptr) {
+        const int step = ld_volatile(p.dev_step);
+        if (step < p.trace_steps) {
+            tr = p.trace + ((size_t)step * gridDim.x + blockIdx.x) * kTraceWords;
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            tr[0] = globaltimer_ns(); tr[1] = tr[2] = tr[3] = 0; tr[4] = smid; tr[5] = 0;
+        }
+    }
+#define NBX_STAMP(k) do { if (tid == 0 && tr) tr[k] = globaltimer_ns(); } while (0)
+#define NBX_MARK(k, v) do { if (tid == 0 && tr) tr[k] = (v); } while (0)
+#else
+#define NBX_STAMP(k) ((void)0)
+#define NBX_MARK(k, v) ((void)0)
+#endif
     int tile = blockIdx.x, split = 0, nsplit = 1, contributors = 1;
     if (tile >= p.whole_tiles) {
         const int r = tile - p.whole_tiles;
@@ -311,6 +332,9 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     }
 #pragma unroll
     for (int b = 0; b < R; ++b) ax[b] = ay[b] = az[b] = make_float2(0.f, 0.f);
+    float2 as[(MATH & 128) ? R : 1];
+#pragma unroll
+    for (int b = 0; b < ((MATH & 128) ? R : 1); ++b) as[b] = make_float2(0.f, 0.f);
     const float2 eps2v = make_float2(p.eps2, p.eps2);
 
     // ---- sweep the j tiles
@@ -324,6 +348,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         }
         const int st = t % STAGES;
         mbar_wait(&full[st], (t / STAGES) & 1);
+        if (t == 0) NBX_STAMP(1);
         const float4 *rec = tiles + st * TJ;
         const int nrec = min(TJ, je - (jb + t * TJ)) >> 1;  // records in this tile (multiple of 4)
 #pragma unroll 1
@@ -353,11 +378,25 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                         const float2 mi = __fmul2_rn(mj, sv[b]);
                         sv[b] = __fmul2_rn(inv2, mi);
                     }
+                    if (MATH & 128) {
+                        // ablation: accumulate sum s*r_j and sum s (the j operand is shared by the R bodies, so the
+                        // accumulate reads two fresh 64-bit registers instead of three); a_i = sum s r_j - r_i sum s
+                        // is formed once at the end.  One more FP32 instruction per pair (13 instead of 12).
 #pragma unroll
-                    for (int b = 0; b < R; ++b) {
-                        ax[b] = __ffma2_rn(dx[b], sv[b], ax[b]);
-                        ay[b] = __ffma2_rn(dy[b], sv[b], ay[b]);
-                        az[b] = __ffma2_rn(dz[b], sv[b], az[b]);
+                        for (int b = 0; b < R; ++b) ax[b] = __ffma2_rn(xj, sv[b], ax[b]);
+#pragma unroll
+                        for (int b = 0; b < R; ++b) ay[b] = __ffma2_rn(yj, sv[b], ay[b]);
+#pragma unroll
+                        for (int b = 0; b < R; ++b) az[b] = __ffma2_rn(zj, sv[b], az[b]);
+#pragma unroll
+                        for (int b = 0; b < R; ++b) as[b] = __fadd2_rn(as[b], sv[b]);
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < R; ++b) {
+                            ax[b] = __ffma2_rn(dx[b], sv[b], ax[b]);
+                            ay[b] = __ffma2_rn(dy[b], sv[b], ay[b]);
+                            az[b] = __ffma2_rn(dz[b], sv[b], az[b]);
+                        }
                     }
                 } else
 #pragma unroll
@@ -398,6 +437,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         if ((tid & 31) == 0) mbar_arrive(&empty[st]);
     }
 
+    NBX_STAMP(2);
     // ---- fold the two j lanes
     float fx[R], fy[R], fz[R];
 #pragma unroll
@@ -407,6 +447,11 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
             fx[b] = ntiles > 0 ? (float)h[0] : 0.f;
             fy[b] = ntiles > 0 ? (float)h[THREADS] : 0.f;
             fz[b] = ntiles > 0 ? (float)h[2 * THREADS] : 0.f;
+        } else if (MATH & 128) {
+            const float ssum = as[b].x + as[b].y;
+            fx[b] = fmaf(nx[b].x, ssum, ax[b].x + ax[b].y);     // nx = -x_i
+            fy[b] = fmaf(ny[b].x, ssum, ay[b].x + ay[b].y);
+            fz[b] = fmaf(nz[b].x, ssum, az[b].x + az[b].y);
         } else {
             fx[b] = ax[b].x + ax[b].y;
             fy[b] = ay[b].x + ay[b].y;
@@ -438,7 +483,8 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
             *s_flag = (arrived == contributors - 1);
         }
         __syncthreads();
-        if (!*s_flag) return;
+        if (!*s_flag) { NBX_STAMP(3); return; }
+        NBX_MARK(5, 1);
         __threadfence();
         if (tid == 0) *ticket = 0;
 #pragma unroll
@@ -496,6 +542,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         e += (double)(v1.w * (v1.x * v1.x + v1.y * v1.y + v1.z * v1.z));
     }
     if (p.acc_out != nullptr) return;
+    NBX_STAMP(3);
 
     // ---- kinetic energy: warp shuffle -> smem -> per-tile partial -> last CTA sums in order
 #pragma unroll

@@ -77,13 +77,15 @@ def barrier():
         dist.barrier()
 
 
-def make_sharded_context(nbx, n: int, exchange: int, device: int | None = None, **ctx_kw):
-    """Create this rank's nbx.Context (i-shard rank/world) and wire the exchange:
-    NCCL unique id broadcast from rank 0, and for P2P the all-gather of handle blobs.
+def make_sharded_context(nbx, n: int, exchange: int | None = None, device: int | None = None, **ctx_kw):
+    """Create this rank's nbx.Context (i-shard rank/world) and wire the exchange (default: the
+    library's default, P2P): NCCL unique id broadcast from rank 0, and for P2P the all-gather of handle blobs.
     If ANY rank cannot map its peers' buffers (no peer access / IPC in this container), every
     rank switches to the NCCL all-gather together -- both are GPU paths; `ctx.exchange_used`
     says which one runs."""
     rank, local_rank, world = env_world()
+    if exchange is None:
+        exchange = nbx.EXCHANGE_P2P
     ctx = nbx.Context(n, device=local_rank if device is None else device, rank=rank, world=world, **ctx_kw)
     ctx.exchange_used = exchange if world > 1 else None
     if world > 1:

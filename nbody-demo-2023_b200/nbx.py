@@ -28,7 +28,7 @@ P2P_BLOB_BYTES = 256
 # every symbol include/nbx.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "nbx_abi_version", "nbx_last_error", "nbx_device_count", "nbx_create", "nbx_destroy",
-    "nbx_set_option", "nbx_get_info", "nbx_plan", "nbx_variant_count", "nbx_variant_name", "nbx_upload",
+    "nbx_set_option", "nbx_get_info", "nbx_plan", "nbx_trace_read", "nbx_variant_count", "nbx_variant_name", "nbx_upload",
     "nbx_download", "nbx_upload_sharded", "nbx_upload_group", "nbx_download_shard", "nbx_run", "nbx_accelerations", "nbx_simulate", "nbx_comm_unique_id",
     "nbx_comm_init", "nbx_comm_init_all", "nbx_run_group", "nbx_p2p_export", "nbx_p2p_attach",
     "nbx_ic_uniform", "nbx_ic_plummer", "nbx_gflop_per_step", "nbx_host_alloc", "nbx_host_free",
@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
         L.nbx_get_info.argtypes = [C.c_void_p, C.POINTER(Info)]
         L.nbx_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.POINTER(Info)]
         L.nbx_upload.argtypes = [C.c_void_p] + [_f32p] * 7
+        L.nbx_trace_read.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.nbx_download.argtypes = [C.c_void_p] + [_f32p] * 6
         L.nbx_upload_sharded.argtypes = [C.c_void_p] + [_f32p] * 7
         L.nbx_upload_group.argtypes = [C.POINTER(C.c_void_p), C.c_int] + [_f32p] * 7
@@ -208,6 +209,16 @@ class Context:
         secs = C.c_double(0.0)
         _check(lib().nbx_run(self._h, nsteps, ke.ctypes.data_as(_f64p), C.byref(secs)))
         return ke[:nsteps], secs.value
+
+    def trace(self):
+        """Trace build only: uint64[steps, ctas, 6] of per-CTA %globaltimer stamps (see nbx_trace_read)."""
+        steps, ctas = C.c_int(0), C.c_int(0)
+        rc = lib().nbx_trace_read(self._h, None, 0, C.byref(steps), C.byref(ctas))
+        if rc == ERR_STATE:
+            _check(rc)
+        buf = np.zeros(max(1, steps.value * ctas.value * 6), dtype=np.uint64)
+        _check(lib().nbx_trace_read(self._h, buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), buf.size, C.byref(steps), C.byref(ctas)))
+        return buf.reshape(steps.value, ctas.value, 6)
 
     def accelerations(self):
         cnt = self.info()["i_count"]

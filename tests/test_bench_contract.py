@@ -40,7 +40,7 @@ def test_reference_arm_other_ranks_stay_silent():
 
 @pytest.mark.gpu
 def test_native_arm_line():
-    d = _run(["--steps", "1", "--warmup", "3", "--no-cpu-baseline"])
+    d = _run(["--steps", "1", "--warmup", "3", "--no-cpu-baseline", "--no-extras"])
     assert (COMMON - {"cpu_baseline"}) <= set(d) and "impl" not in d
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 3 and d["dtype"] == "f32"
     assert d["gpu_launches"] == 1
@@ -51,3 +51,23 @@ def test_native_arm_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 7 * 4 * (1 << 20) and d["e2e"]["value"] > 0.9 * d["value"]
     assert d["clocks"]["sm_max_mhz"] and "reasons" in d["clocks"]
     assert d["config"]["n_bodies"] == 1 << 20
+    # correctness of what was timed rides on the line: reference output, fp64 sums, sampled forces
+    p = d["parity"]
+    assert p["ok"] is True and p["vs_reference_output"]["ok"] is True and p["vs_reference_output"]["kenergy_max_rel"] < 1e-4
+    assert p["sampled_forces"]["ok"] is True and p["kenergy_vs_fp64_sum"] < 1e-6
+
+
+@pytest.mark.gpu
+def test_native_arm_default_line_carries_the_other_configs():
+    """The default 1-GPU run also times C3 (the strong-scaling anchor), C1 and C0 and the reference's CUDA
+    backend, each outside the headline's timed region."""
+    d = _run(["--steps", "2", "--warmup", "3", "--no-cpu-baseline"], timeout=900)
+    a = d["config"]["strong_anchor"]
+    assert a["workload"].startswith("C3") and 4000 < a["ms_per_step"] < 12000 and a["parity"]["ok"] is True
+    c1, c0 = d["also"]["c1"], d["also"]["c0"]
+    assert c1["n_bodies"] == 16384 and 0.05 < c1["ms_per_step"] < 0.2 and c1["parity"]["ok"] is True
+    assert c1["parity"]["vs_reference_output"]["steps"] == 500
+    assert c0["n_bodies"] == 2000 and c0["ms_per_step"] < 0.05 and c0["parity"]["ok"] is True
+    g = d["gpu_reference"]
+    assert g["kernel_only"]["value"] >= g["end_to_end"]["value"] > 0
+    assert g["this_build_same_n"]["kernel_only"] > g["kernel_only"]["value"]

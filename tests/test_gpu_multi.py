@@ -43,12 +43,13 @@ def test_one_process_group_matches_single_gpu(nbx, world, exchange):
         for c in ctxs:
             c.set_option("j_splits", splits)
             c.set_option("exchange", XCH[exchange])
-            c.upload(*arrs)
-        nbx.comm_init_all(ctxs)
-        if exchange == "p2p":
-            blobs = b"".join(c.p2p_export() for c in ctxs)
+        if exchange != "p2p":          # the P2P group needs no communicator and attaches itself
+            nbx.comm_init_all(ctxs)
+        if world == 4:
+            nbx.upload_group(ctxs, *arrs)      # sharded: each GPU takes its own slice over PCIe
+        else:
             for c in ctxs:
-                c.p2p_attach(blobs)
+                c.upload(*arrs)
         ke, secs = nbx.run_group(ctxs, steps)
         out = [np.zeros(n, dtype=np.float32) for _ in range(6)]
         for c in ctxs:            # each rank fills positions (all) and its own velocity range
@@ -79,13 +80,20 @@ def test_cli_multi_gpu(pkg, nbx):
     if _ngpu(nbx) < 2:
         pytest.skip("needs 2 GPUs")
     outs = {}
-    for g, x in ((1, "nccl"), (2, "nccl"), (2, "p2p"), (2, "nccl_overlap")):
-        env = dict(os.environ, NBODY_GPUS=str(g), NBODY_SFREQ="5", NBODY_EXCHANGE=x, NBODY_JSPLITS="2", NBODY_GRAPH="0")
+    for g, x in ((1, "nccl"), (2, "nccl"), (2, "p2p"), (2, "nccl_overlap"), (2, None)):
+        env = dict(os.environ, NBODY_GPUS=str(g), NBODY_SFREQ="5", NBODY_JSPLITS="2", NBODY_GRAPH="0", NCCL_DEBUG="VERSION")
+        env.pop("NBODY_EXCHANGE", None)
+        if x:
+            env["NBODY_EXCHANGE"] = x
         r = subprocess.run([pkg.CLI_PATH, "4096", "10"], capture_output=True, text=True, env=env, timeout=300)
         assert r.returncode == 0, r.stderr
         outs[(g, x)] = [l.split()[2] for l in r.stdout.splitlines() if re.match(r"^ \d+", l)]
         assert f"# Number GPUs        : {g}" in r.stdout
-    assert outs[(1, "nccl")] == outs[(2, "nccl")] == outs[(2, "p2p")]
+        # stdout stays byte-compatible: banner, header and rule lines first, nothing from NCCL in between
+        assert r.stdout.splitlines()[:3] == ["===============================", " Initialize Gravity Simulation",
+                                             " nPart = 4096; nSteps = 10; dt = 0.1"]
+        assert "NCCL version" not in r.stdout
+    assert outs[(1, "nccl")] == outs[(2, "nccl")] == outs[(2, "p2p")] == outs[(2, None)]
     for a, b in zip(outs[(1, "nccl")], outs[(2, "nccl_overlap")]):
         assert abs(float(a) - float(b)) / float(a) < 1e-4      # 5-digit column, other summation order
 
@@ -109,8 +117,13 @@ n, steps = 4992, 5      # multiple of 8*world: same padding, hence same j-split 
 arrs = nbx.ic(n)
 ctx = dist.make_sharded_context(nbx, n, {XCH[exchange]})
 ctx.set_option("j_splits", 2)
-ctx.upload(*arrs)
-dist.barrier()
+if rank == 0:
+    import time; time.sleep(1.0)     # rank 1 reaches nbx_run while rank 0 is still uploading: the library orders it
+if {XCH[exchange]} == 0:
+    ctx.upload_sharded(*arrs)        # collective: own shard over PCIe, packed records over NVLink
+else:
+    ctx.upload(*arrs)                # P2P: nbx_run's in-stream barrier keeps rank 1 from storing into rank 0's
+                                     # replica before rank 0 has packed it
 ke, secs = ctx.run(steps)
 st = ctx.state()
 i0, cnt = ctx.info()["i_begin"], ctx.info()["i_count"]
@@ -138,3 +151,101 @@ torch.distributed.destroy_process_group()
             for k, f in enumerate(("px", "py", "pz")):
                 assert np.array_equal(d[f], st1[k])
             assert np.array_equal(d["vx"][i0:hi], st1[3][i0:hi])
+
+
+# ------------------------------------------------------------------------------------------
+#  the DEFAULT plan (no pinned j_splits) on several GPUs, against output of the reference itself
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world,name", [(2, "c2"), (4, "c2"), (8, "c3"), (2, "n262144")])
+def test_default_plan_multi_gpu_vs_reference_fixture(nbx, world, name):
+    """i-sharded runs with the plan nbx_run picks by itself (at C2 on 2 GPUs and C3 on 8 GPUs: 444 unsplit
+    tiles + 68 split 37 ways per GPU; default P2P exchange) against ver8's kinetic energies and sampled
+    positions (tests/golden/large_*_ver8.npz): the north star's 1e-4 gates."""
+    from test_gpu_headline import check_against_fixture, load
+    if _ngpu(nbx) < world:
+        pytest.skip(f"needs {world} GPUs")
+    fx = load(name)
+    n, steps = int(fx["n"]), int(fx["steps"])
+    arrs = nbx.ic(n, str(fx["ic"]))
+    ctxs = [nbx.Context(n, device=g, rank=g, world=world) for g in range(world)]
+    try:
+        nbx.upload_group(ctxs, *arrs)
+        ke, secs = nbx.run_group(ctxs, steps)
+        info = ctxs[0].info()
+        assert info["exchange"] == nbx.EXCHANGE_P2P
+        if name != "n262144":
+            assert 0 < info["whole_tiles"] < info["i_tiles"] and info["j_splits"] > 1
+        out = [np.zeros(n, dtype=np.float32) for _ in range(6)]
+        for c in ctxs:
+            c.download_shard(*out)          # every rank contributes its own slice of all six arrays
+        check_against_fixture(fx, ke, out, f"{name} on {world} GPUs, default plan")
+        ref = ctxs[0].state()
+        for c in ctxs[1:]:                  # replicas agree bit for bit
+            for a, b in zip(c.state()[:3], ref[:3]):
+                assert np.array_equal(a, b)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_peer_timeout_is_an_error_not_a_hang(nbx):
+    """A peer that never steps: the waiting GPU's kernel gives up after peer_timeout_ms, nbx_run returns
+    NBX_ERR_PEER and the context stays poisoned.  Both shards live on GPU 0 here (same-device peers
+    are plain pointers), so this runs on a 1-GPU box; rank 1 is attached and then never run."""
+    import time
+    n = 4096
+    arrs = nbx.ic(n)
+    a = nbx.Context(n, device=0, rank=0, world=2)
+    b = nbx.Context(n, device=0, rank=1, world=2)
+    try:
+        blobs = a.p2p_export() + b.p2p_export()
+        for c in (a, b):
+            c.set_option("exchange", nbx.EXCHANGE_P2P)
+            c.p2p_attach(blobs)
+            c.upload(*arrs)
+        a.set_option("peer_timeout_ms", 250)
+        t0 = time.time()
+        with pytest.raises(nbx.NbxError) as e:
+            a.run(3)                        # step 0 runs (epoch 0), step 1 waits for rank 1's step 0: never comes
+        dt = time.time() - t0
+        assert e.value.code == nbx.ERR_PEER and "peer rank 1" in str(e.value)
+        assert 0.2 < dt < 20.0
+        assert a.info()["device_error"] & 0xff == 1
+        with pytest.raises(nbx.NbxError) as e2:
+            a.run(1)
+        assert e2.value.code == nbx.ERR_PEER
+        # rank 1's context is untouched and the GPU is healthy: a fresh single-GPU run still works
+        with nbx.Context(n) as c:
+            c.upload(*arrs)
+            ke, _ = c.run(2)
+            assert np.all(np.isfinite(ke))
+    finally:
+        a.close()
+        b.close()
+
+
+def test_sharded_upload_equals_full_upload(nbx):
+    world = min(_ngpu(nbx), 4)
+    if world < 2:
+        pytest.skip("needs 2 GPUs")
+    n = 10007                                  # ragged: padding in the last shard
+    arrs = nbx.ic(n)
+    ctxs = [nbx.Context(n, device=g, rank=g, world=world) for g in range(world)]
+    try:
+        nbx.upload_group(ctxs, *arrs)
+        for c in ctxs:
+            st = c.state()
+            lo, cnt = c.info()["i_begin"], c.info()["i_count"]
+            for k in range(3):
+                assert np.array_equal(st[k], arrs[k])
+            hi = min(lo + cnt, n)
+            for k in range(3, 6):
+                assert np.array_equal(st[k][lo:hi], arrs[k][lo:hi])
+            sh = [np.full(n, -7.0, dtype=np.float32) for _ in range(6)]
+            c.download_shard(*sh)
+            for k in range(6):
+                assert np.array_equal(sh[k][lo:hi], arrs[k][lo:hi])
+                assert np.all(sh[k][:lo] == -7.0) and np.all(sh[k][hi:] == -7.0)
+    finally:
+        for c in ctxs:
+            c.close()

@@ -123,3 +123,52 @@ def test_oracle_bit_exact_vs_compiled_reference(oracle, variant, n, steps):
     assert ke[-1] == ke_ref
     for f in oracle.State.FIELDS:
         assert np.array_equal(getattr(s, f), getattr(ref, f)), f
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("ver,n,steps", [("ver8", 4096, 5), ("ver7", 3000, 4), ("ver2", 1000, 3)])
+def test_reference_from_arbitrary_state_equals_its_own_run(oracle, ver, n, steps):
+    """ref_state_verN (the unmodified reference step loop fed an input state, one start() per step)
+    must reproduce ref_dump_verN (the reference run as it is) bit for bit from the same ICs."""
+    s0 = oracle.ic_uniform(n)
+    a, ke, _ = oracle.ref_state_run(ver, s0, steps, threads=4)
+    b, ke_b, _ = oracle.ref_run(ver, n, steps, threads=4)
+    for f in oracle.State.FIELDS:
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert ke.size == steps and abs(float(ke[-1]) - float(ke_b)) <= 2e-7 * float(ke_b)   # omp reduction order
+    # and restarting from a dumped state continues the run exactly
+    mid, _, _ = oracle.ref_state_run(ver, s0, 2, threads=4)
+    end, _, _ = oracle.ref_state_run(ver, mid, steps - 2, threads=4)
+    for f in oracle.State.FIELDS:
+        assert np.array_equal(getattr(end, f), getattr(a, f)), f
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference only exists in the build container")
+def test_reference_runs_plummer_state_and_oracle_agrees(oracle, nbx):
+    """Inputs the reference cannot generate itself (Plummer ICs) reach it through ref_state_ver8; the C
+    restatement (ver7 order) agrees with it to the reference's own version-to-version noise."""
+    n = 4096
+    arrs = nbx.ic(n, "plummer")
+    s0 = oracle.State(n)
+    for f, a in zip(oracle.State.FIELDS, arrs):
+        setattr(s0, f, a.copy())
+    ref, ke_ref, _ = oracle.ref_state_run("ver8", s0, 3, threads=4)
+    s = s0.copy()
+    ke = oracle.run(s, 3, variant="ver7")
+    assert np.max(np.abs(ke - ke_ref) / ke_ref) < 5e-6
+    assert rel_l2(s.pos(), ref.pos()) < 1e-6
+
+
+def test_large_fixtures_are_consistent_with_the_small_ones(golden):
+    """tests/golden/large_*_ver8.npz (make_golden_large.py) against golden.json (make_golden.py): the first
+    three kinetic energies of the 16384-body run were recorded by both generators."""
+    import os
+    from conftest import GOLDEN_DIR
+    fx = np.load(os.path.join(GOLDEN_DIR, "large_c1_ver8.npz"))
+    want = np.array(golden["c1"]["kenergy_steps_1_3_ver8"])
+    assert np.max(np.abs(fx["ke"][:3] - want) / want) < 1e-6
+    assert int(fx["n"]) == 16384 and int(fx["steps"]) == 500 and fx["ke"].size == 500 and fx["sel"].size == 4096
+    for name, n, steps in (("n262144", 262144, 10), ("c2", 1 << 20, 2)):
+        f = np.load(os.path.join(GOLDEN_DIR, f"large_{name}_ver8.npz"))
+        assert int(f["n"]) == n and f["ke"].size == steps and f["pos_sel"].shape == (4096, 3)
+        assert np.all(np.diff(f["sel"]) > 0) and np.all(np.isfinite(f["ke"]))
