@@ -86,6 +86,9 @@ typedef struct nbx_info {
     int device_error;       /* last device error word (0 = none): low byte 1 = peer timeout
                                (peer rank << 8), 2 = aborted, 3 = debug check (source line << 8) */
     int peer_timeout_ms;    /* bound on the in-kernel wait for a peer's previous step */
+    int multicast;          /* 1: the P2P exchange goes through an NVSwitch multicast mapping (one
+                               multimem.st per record instead of world-1 NVLink stores) */
+    int reserved;
 } nbx_info;
 
 /* ---- library ---------------------------------------------------------------- */
@@ -109,6 +112,9 @@ NBX_API void nbx_destroy(nbx_ctx *ctx);
  *   "graph"     1/0 replay steps from a CUDA graph (auto: on for small N)
  *   "accurate"  1/0 two-level accumulation (float per j tile, then double): large-N accuracy option
  *   "pdl"       1/0 programmatic dependent launch between consecutive steps (-1 = auto: many-wave grids only)
+ *   "multicast" P2P exchange inside one process (nbx_run_group): -1 auto = use NVSwitch multicast
+ *               (cuMulticast* + multimem.st) when the driver offers it, 0 never, 1 fail if unavailable;
+ *               NBX_VERBOSE=1 prints why it was not used
  *   "smem_pad_kb"  extra dynamic shared memory per CTA in KiB (tuning: caps the resident CTAs per SM)
  *   "exchange"  NBX_EXCHANGE_* (default NBX_EXCHANGE_P2P)
  *   "peer_timeout_ms"  P2P exchange: how long a step may wait inside the kernel for a peer GPU to

@@ -8,6 +8,7 @@
 #include "../../include/nbx.h"
 #include "ic.hpp"
 #include "nbx_kernels.cuh"
+#include "nbx_multicast.hpp"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -118,10 +119,14 @@ static const std::vector<Variant> &variants()
 {
     static const std::vector<Variant> v = {
         // shapes: r<i-bodies per thread>_t<threads>_u<j-records per trip>; "_stage" = stage-major source
-        // order of the inner loop (+1% over body-major in same-box A/B, profiles/r01_ab_*.log)
-        make_variant<2, 256, 256, 4, 4, 2, 16>("r4_t256_u4_stage"),   // [0] default for large shards (kLargeVariant)
-        make_variant<1, 128, 256, 4, 4, 6>("r2_t128_u4"),             // [1] default for small shards (kSmallVariant)
-        make_variant<2, 256, 256, 4, 4, 2, 48>("r4_t256_u4_stage_acc64"),   // [2] accuracy option (kAccurateVariant)
+        // order of the inner loop (+1% over body-major in same-box A/B, profiles/r01_ab_*.log);
+        // "_f2" = two-level float accumulation (lane sums folded into a second float in shared memory every
+        // 64 j tiles): removes the systematic low bias of long float sums for 0.4% of throughput
+        // (profiles/r02d_*: N = 1 M kinetic energy 2e-7 from the fp64 truth instead of 1.8e-4)
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024>("r4_t256_u4_stage_f2"),   // [0] default for large shards (kLargeVariant)
+        make_variant<1, 128, 256, 4, 4, 6>("r2_t128_u4"),                            // [1] default for small shards (kSmallVariant)
+        make_variant<2, 256, 256, 4, 4, 2, 48>("r4_t256_u4_stage_acc64"),            // [2] accuracy option (kAccurateVariant)
+        make_variant<2, 256, 256, 4, 4, 2, 16>("r4_t256_u4_stage"),                  // [3] one float accumulator per lane, like the reference's loops
         // CTA sizes the ver5_all-style CLI can ask for (argv[5] = thread_dim0, cuda/Compute.cu:137-145)
         make_variant<2, 128, 256, 4, 2, 4>("r4_t128_u2"),
         make_variant<2, 512, 512, 4, 2, 1>("r4_t512_u2"),
@@ -131,19 +136,24 @@ static const std::vector<Variant> &variants()
         // builds libnbx_ablation.so with them; the product library does not carry them.
         make_variant<2, 256, 256, 4, 2, 2>("r4_t256_u2"),
         make_variant<2, 256, 256, 4, 2, 2, 16>("r4_t256_u2_stage"),
+        make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024>("r4_t256_u2_stage_f2"),
+        make_variant<2, 256, 256, 4, 4, 2, 256 | 1024>("r4_t256_u4_f2"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256>("r4_t256_u4_stage_f2p4"),           // fold every 4 tiles: -3%
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 512>("r4_t256_u4_stage_f2p16"),    // every 16: -0.5%
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1536>("r4_t256_u4_stage_f2p256"),
         make_variant<2, 256, 256, 4, 4, 2>("r4_t256_u4"),
         make_variant<2, 256, 256, 4, 1, 2>("r4_t256_u1"),
         make_variant<3, 256, 256, 4, 2, 2>("r6_t256_u2"),
         make_variant<4, 256, 256, 4, 1, 1>("r8_t256_u1"),
         make_variant<1, 256, 256, 4, 4, 3>("r2_t256_u4"),
-        make_variant<2, 256, 256, 4, 2, 2, 1>("r4_t256_u2_sacc"),     // scalar accumulate
-        make_variant<2, 256, 256, 4, 2, 2, 15>("r4_t256_u2_scalar"),  // no packed FP32 at all
-        make_variant<2, 256, 256, 4, 2, 3, 16>("r4_t256_u2_stage_occ3"),   // 3 CTAs/SM x 85 registers
-        make_variant<2, 256, 256, 4, 1, 3, 16>("r4_t256_u1_stage_occ3"),
-        make_variant<2, 256, 256, 4, 4, 2, 16 | 128>("r4_t256_u4_stage_xjacc"),   // accumulate sum s*r_j, sum s (13 ops/pair)
-        make_variant<2, 256, 256, 4, 2, 2, 16 | 128>("r4_t256_u2_stage_xjacc"),
-        make_variant<2, 256, 256, 8, 4, 2, 16>("r4_t256_u4_stage_s8"),            // deeper TMA ring
-        make_variant<2, 256, 512, 4, 4, 2, 16>("r4_t256_u4_stage_tj512"),         // larger TMA tiles
+        make_variant<2, 256, 256, 4, 2, 2, 1>("r4_t256_u2_sacc"),                        // scalar accumulate
+        make_variant<2, 256, 256, 4, 2, 2, 15>("r4_t256_u2_scalar"),                     // no packed FP32 at all
+        make_variant<2, 256, 256, 4, 2, 3, 16>("r4_t256_u2_stage_occ3"),                 // 3 CTAs/SM x 78 registers: -3%
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 128>("r4_t256_u4_stage_xjacc"),          // accumulate sum s*r_j, sum s: 13 ops/pair, -7%, 4e-3 force error at 1 M
+        make_variant<4, 256, 256, 4, 2, 1, 16>("r8_t256_u2_stage"),                      // 8 bodies per thread, 8 warps/SM: no better at any N
+        make_variant<3, 256, 256, 4, 2, 1, 16>("r6_t256_u2_stage"),
+        make_variant<2, 256, 256, 8, 4, 2, 16>("r4_t256_u4_stage_s8"),                   // deeper TMA ring: no change
+        make_variant<2, 256, 512, 4, 4, 2, 16>("r4_t256_u4_stage_tj512"),                // larger TMA tiles: no change
 #endif
     };
     return v;
@@ -184,6 +194,8 @@ struct nbx_ctx {
     int device_error = 0;              // last value read from counters[3]; non-zero = poisoned
     bool debug_fault = false;          // debug build only
     int smem_pad = 0;                  // tuning knob ("smem_pad_kb")
+    int auto_pad = 0;                  // single-wave grids: pad so that one CTA owns an SM (see resolve)
+    bool single_wave = false;
     unsigned long long *trace = nullptr;   // trace build only
     int trace_steps = 0, trace_ctas = 0;
     bool resolved = false;
@@ -202,6 +214,10 @@ struct nbx_ctx {
     float4 *peer_pos[2][nbx::kMaxWorld] = {};
     int *peer_flags[nbx::kMaxWorld] = {};
     std::vector<void *> ipc_opened;
+    nbx_mc::Buffer mcbuf[2];                     // NVSwitch multicast mappings of pos[0], pos[1] (when mc_active)
+    bool mc_active = false;
+    std::string mc_note = "not attempted";
+    int opt_multicast = -1;                      // -1 auto (try it inside one process), 0 off, 1 required
 
     long long kernel_launches = 0, aux_launches = 0;
     double last_run_seconds = 0.0, kernel_seconds_total = 0.0;
@@ -294,9 +310,18 @@ static int resolve(nbx_ctx *c)
     const int splits = pl.j_splits;
     const Variant &v = variants()[c->variant];
     CU(cudaSetDevice(c->device));
-    CU(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem + c->smem_pad));
+    // A grid that fits the SMs once (small N: 144 CTAs at N = 16 384) runs one CTA per SM.  Consecutive
+    // steps then overlap best with programmatic dependent launch -- but only if a dependent CTA cannot
+    // squeeze in NEXT to a running one (traced: it did, two CTAs shared 72 SMs and the step took 0.20 ms
+    // instead of 0.114).  Padding the dynamic shared memory past half an SM's worth makes residency 1;
+    // the dependents then start exactly as SMs drain (profiles/r02_trace_c1.log: 117.0 -> 115.8 us).
+    const int ctas_total = c->whole_tiles + (c->i_tiles - c->whole_tiles) * c->j_splits;
+    c->single_wave = ctas_total <= c->sm_count && c->opt_pdl != 0 && c->smem_pad == 0 &&
+                     !(c->world > 1 && c->exchange == NBX_EXCHANGE_NCCL_OVERLAP);
+    c->auto_pad = c->single_wave ? std::max(0, 117 * 1024 - v.smem) : 0;
+    CU(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem + c->smem_pad + c->auto_pad));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, v.threads, v.smem + c->smem_pad));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, v.threads, v.smem + c->smem_pad + c->auto_pad));
     if (occ < 1) return fail(NBX_ERR_CUDA, "kernel variant %s cannot be resident", v.name);
     c->ctas_per_sm = occ;
 
@@ -348,6 +373,8 @@ static void fill_params(const nbx_ctx *c, StepParams &p, int in_buf, float4 *acc
     p.whole_tiles = c->whole_tiles;
     p.j_splits = c->j_splits;
     p.split_bodies = c->split_bodies;
+    // partial scratch beyond ~16 MB does not stay in L2 between its producer and its consumer anyway
+    p.discard_partials = ((size_t)c->j_splits * c->split_bodies * sizeof(float4) > ((size_t)16 << 20)) ? 1 : 0;
     p.j_org = 0;
     p.j_len = c->n_pad;
     p.split_base = 0;
@@ -373,6 +400,7 @@ static void fill_params(const nbx_ctx *c, StepParams &p, int in_buf, float4 *acc
             p.peer_flags[g] = c->peer_flags[g];
         }
         p.my_flags = c->flags;
+        p.mc_pos_out = c->mc_active ? reinterpret_cast<float4 *>(c->mcbuf[in_buf ^ 1].mcva) : nullptr;
     }
 }
 
@@ -386,16 +414,15 @@ static int launch_step(nbx_ctx *c, int in_buf, float4 *acc_out = nullptr, int ph
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
     cfg.blockDim = dim3(v.threads);
-    cfg.dynamicSmemBytes = v.smem + c->smem_pad;
+    cfg.dynamicSmemBytes = v.smem + c->smem_pad + c->auto_pad;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap our prologue with
     attr[0].val.programmaticStreamSerializationAllowed = 1;            // the previous step's tail
     cfg.attrs = attr;
-    // Auto: only for grids of many waves.  With a single under-subscribed wave (N = 16 384: 144 CTAs)
-    // the early-scheduled dependents take the free slots unevenly and the next step runs two CTAs
-    // on some SMs and none on others: measured 0.19 ms instead of 0.114 ms per step.
-    const bool pdl = c->opt_pdl >= 0 ? c->opt_pdl != 0 : ctas >= 4 * c->sm_count;
+    // Auto: grids of many waves, and single-wave grids made one-CTA-per-SM by resolve().  In between
+    // (a wave or two, two CTAs per SM) early-scheduled dependents take the free slots unevenly.
+    const bool pdl = c->opt_pdl >= 0 ? c->opt_pdl != 0 : (ctas >= 4 * c->sm_count || c->single_wave);
     cfg.numAttrs = pdl ? 1 : 0;
     CU(cudaLaunchKernelExC(&cfg, v.fn, args));
     c->kernel_launches++;
@@ -641,7 +668,12 @@ void nbx_destroy(nbx_ctx *c)
     if (c->graph16) cudaGraphExecDestroy(c->graph16);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
-    cudaFree(c->pos[0]); cudaFree(c->pos[1]); cudaFree(c->vel); cudaFree(c->part); cudaFree(c->acc);
+    if (c->mc_active) {            // the replicas live in driver-API allocations bound to the multicast team
+        nbx_mc::release(c->mcbuf[0]); nbx_mc::release(c->mcbuf[1]);
+    } else {
+        cudaFree(c->pos[0]); cudaFree(c->pos[1]);
+    }
+    cudaFree(c->vel); cudaFree(c->part); cudaFree(c->acc);
     cudaFree(c->tile_ticket); cudaFree(c->ke_part); cudaFree(c->counters); cudaFree(c->flags);
     cudaFree(c->ke_dev); cudaFree(c->stage); cudaFree(c->trace);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -676,6 +708,9 @@ int nbx_set_option(nbx_ctx *c, const char *key, long long value)
         if (value < 0 || value > 4096) return fail(NBX_ERR_ARG, "trace_steps out of range");
         c->trace_steps = (int)value;
 #endif
+    } else if (k == "multicast") {     // NVSwitch multicast for the P2P exchange: -1 auto, 0 never, 1 fail if unavailable
+        c->opt_multicast = value < 0 ? -1 : (value ? 1 : 0);
+        return NBX_OK;
     } else if (k == "smem_pad_kb") {   // extra dynamic shared memory per CTA: lowers the resident CTAs per SM
         if (value < 0 || value > 200) return fail(NBX_ERR_ARG, "smem_pad_kb out of range");
         c->smem_pad = (int)value * 1024;
@@ -714,6 +749,7 @@ int nbx_get_info(const nbx_ctx *c, nbx_info *o)
     o->kernel_launches = c->kernel_launches; o->aux_launches = c->aux_launches;
     o->last_run_seconds = c->last_run_seconds; o->kernel_seconds_total = c->kernel_seconds_total;
     o->device_error = c->device_error; o->peer_timeout_ms = c->peer_timeout_ms;
+    o->multicast = c->mc_active ? 1 : 0;
     return NBX_OK;
 }
 
@@ -979,9 +1015,54 @@ int nbx_run(nbx_ctx *c, int nsteps, double *kenergy_out, double *seconds_out)
     return NBX_OK;
 }
 
+// One process, several GPUs on an NVSwitch: move the position replicas into allocations bound to a
+// multicast team, so the epilogue exchange is one multimem.st per record instead of world-1 stores.
+// Not being able to is not an error (unless "multicast" = 1): the unicast NVLink stores remain.
+static int try_multicast_group(nbx_ctx **ctxs, int count)
+{
+    if (ctxs[0]->opt_multicast == 0 || ctxs[0]->mc_active) return NBX_OK;
+    std::vector<int> devices((size_t)count);
+    for (int g = 0; g < count; ++g) devices[g] = ctxs[g]->device;
+    bool distinct = true;
+    for (int g = 0; g < count; ++g)
+        for (int h = g + 1; h < count; ++h) distinct = distinct && devices[g] != devices[h];
+    const size_t bytes = (size_t)ctxs[0]->n_pad * sizeof(float4);
+    std::vector<nbx_mc::Buffer> team[2];
+    std::string why = distinct ? "" : "two shards share a GPU";
+    for (int b = 0; b < 2 && why.empty(); ++b) why = nbx_mc::create_team(devices, bytes, team[b]);
+    if (!why.empty()) {
+        for (auto &t : team)
+            for (auto &buf : t) nbx_mc::release(buf);
+        cudaGetLastError();
+        if (ctxs[0]->opt_multicast == 1) return fail(NBX_ERR_CUDA, "NVSwitch multicast required but unavailable: %s", why.c_str());
+        if (std::getenv("NBX_VERBOSE"))
+            std::fprintf(stderr, "nbx: NVSwitch multicast unavailable (%s); the exchange uses unicast NVLink stores\n", why.c_str());
+        for (int g = 0; g < count; ++g) ctxs[g]->mc_note = why;
+        return NBX_OK;
+    }
+    for (int g = 0; g < count; ++g) {
+        nbx_ctx *c = ctxs[g];
+        CU(cudaSetDevice(c->device));
+        CU(cudaStreamSynchronize(c->stream));
+        for (int b = 0; b < 2; ++b) {
+            float4 *fresh = reinterpret_cast<float4 *>(team[b][g].uc);
+            CU(cudaMemcpy(fresh, c->pos[b], bytes, cudaMemcpyDeviceToDevice));
+            CU(cudaFree(c->pos[b]));
+            c->pos[b] = fresh;
+            c->mcbuf[b] = team[b][g];
+        }
+        c->mc_active = true;
+        c->mc_note = "active";
+        c->resolved = false;            // graphs bake the old addresses in
+    }
+    return NBX_OK;
+}
+
 // One process, several GPUs: map every context's replicas and flags into every other context.
 static int attach_group(nbx_ctx **ctxs, int count)
 {
+    int mrc = try_multicast_group(ctxs, count);
+    if (mrc) return mrc;
     std::vector<unsigned char> blobs((size_t)count * NBX_P2P_BLOB_BYTES);
     int rc;
     for (int g = 0; g < count; ++g)

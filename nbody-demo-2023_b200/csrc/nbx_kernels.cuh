@@ -53,6 +53,7 @@ struct StepParams {
     int whole_tiles;        // tiles [0, whole_tiles) are not split along j
     int j_splits;           // split count of tiles [whole_tiles, i_tiles) in THIS launch
     int split_bodies;       // i-bodies covered by split tiles (stride of `part`)
+    int discard_partials;   // 1: the combining CTA drops the consumed partial lines from L2 (large tails only)
     // A launch may cover only a window of the j-bodies (NCCL-overlap mode runs a step as two
     // launches: the rank's own j-shard while the all-gather is in flight, then the rest):
     int j_org, j_len;       // j window = [j_org, j_org + j_len) modulo n_pad (multiples of 8)
@@ -62,6 +63,7 @@ struct StepParams {
     // P2P exchange (world > 1 and exchange == P2P): peers' replicas and completion flags
     int world, rank, p2p;
     float4 *peer_pos_out[kMaxWorld];  // [g] = rank g's pos_out (self entry unused)
+    float4 *mc_pos_out;               // non-null: NVSwitch multicast mapping of pos_out (one store reaches every GPU)
     int *peer_flags[kMaxWorld];       // [g] = rank g's flags[kMaxWorld]; we write slot [rank]
     const int *my_flags;              // this rank's flags[kMaxWorld]
     unsigned long long peer_wait_ns;  // how long a step may wait for a peer's previous step
@@ -135,6 +137,17 @@ __device__ __forceinline__ void st_release_sys(int *p, int v)
 {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// NVSwitch multicast stores (SASS: the store carries the multimem qualifier): one instruction, every GPU
+// of the multicast team receives the data in its own copy of the buffer.
+__device__ __forceinline__ void multimem_st_v4(float4 *mc_ptr, float4 v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void multimem_st_v2(float2 *mc_ptr, float2 v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc_ptr), "f"(v.x), "f"(v.y) : "memory");
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
     unsigned long long t;
@@ -183,7 +196,8 @@ template <bool SCALAR> __device__ __forceinline__ float2 fma2(float2 a, float2 b
 template <int THREADS, int TJ, int STAGES, int R2 = 0, int MATH = 0>
 __host__ __device__ constexpr int step_smem_bytes()
 {
-    return STAGES * TJ * 16 + 2 * STAGES * 8 + (THREADS / 32) * 8 + 16 + ((MATH & 32) ? 3 * 2 * R2 * THREADS * 8 : 0);
+    return STAGES * TJ * 16 + 2 * STAGES * 8 + (THREADS / 32) * 8 + 16 + ((MATH & 32) ? 3 * 2 * R2 * THREADS * 8 : 0) +
+           ((MATH & 256) ? 3 * 2 * R2 * THREADS * 4 : 0);
 }
 
 // ------------------------------------------------------------------------------
@@ -214,6 +228,13 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     // the large-N float summation error (1e-4 at 1 M, 1e-3 at 4 M for the reference's single
     // accumulator) drops to the 1e-6 level for ~1% time.  hi[q * THREADS + tid]: conflict-free.
     double *hi = reinterpret_cast<double *>(smem_raw + step_smem_bytes<THREADS, TJ, STAGES>());
+    // f2 (MATH & 256): two-level FLOAT accumulation, the default.  A single float accumulator per lane is
+    // not just noisy at large N, it is BIASED: summed over 5e5 terms the force magnitude comes out
+    // systematically low (N = 1 M: -2e-5 here, -7e-5 for the reference's own single-accumulator float
+    // loop, measured against fp64 -- tests/golden/truth_*), and the kinetic energy inherits twice that.
+    // Folding the lane sums into a second float per (body, component) in shared memory after every 4th
+    // j tile keeps every float sum <= 1024 terms long; cost: 12 LDS/FADD/STS per 24 576 FP32 instructions.
+    float *hif = reinterpret_cast<float *>(smem_raw + step_smem_bytes<THREADS, TJ, STAGES>());
 
     const int tid = threadIdx.x;
 #ifdef NBX_TRACE
@@ -433,6 +454,18 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                 ax[b] = ay[b] = az[b] = make_float2(0.f, 0.f);
             }
         }
+        constexpr int FOLD = 4 << (2 * ((MATH >> 9) & 3));     // fold period in j tiles: 4 (default), 16, 64, 256
+        if ((MATH & 256) && ((t & (FOLD - 1)) == FOLD - 1 || t == ntiles - 1)) {
+#pragma unroll
+            for (int b = 0; b < R; ++b) {
+                float *h = hif + (3 * b) * THREADS + tid;
+                const bool first = (t < FOLD);
+                h[0] = (first ? 0.f : h[0]) + (ax[b].x + ax[b].y);
+                h[THREADS] = (first ? 0.f : h[THREADS]) + (ay[b].x + ay[b].y);
+                h[2 * THREADS] = (first ? 0.f : h[2 * THREADS]) + (az[b].x + az[b].y);
+                ax[b] = ay[b] = az[b] = make_float2(0.f, 0.f);
+            }
+        }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&empty[st]);
     }
@@ -447,6 +480,11 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
             fx[b] = ntiles > 0 ? (float)h[0] : 0.f;
             fy[b] = ntiles > 0 ? (float)h[THREADS] : 0.f;
             fz[b] = ntiles > 0 ? (float)h[2 * THREADS] : 0.f;
+        } else if (MATH & 256) {
+            const float *h = hif + (3 * b) * THREADS + tid;
+            fx[b] = ntiles > 0 ? h[0] : 0.f;
+            fy[b] = ntiles > 0 ? h[THREADS] : 0.f;
+            fz[b] = ntiles > 0 ? h[2 * THREADS] : 0.f;
         } else if (MATH & 128) {
             const float ssum = as[b].x + as[b].y;
             fx[b] = fmaf(nx[b].x, ssum, ax[b].x + ax[b].y);     // nx = -x_i
@@ -487,19 +525,48 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         NBX_MARK(5, 1);
         __threadfence();
         if (tid == 0) *ticket = 0;
+        // The adds stay in split order (bit-reproducible), but the L2 loads of all R bodies and CH
+        // consecutive splits are issued together: the combine is a chain of L2 round trips on the
+        // step's critical path (traced at N = 16 384: 8 dependent rounds = 4.5 us of a 117 us step),
+        // this makes it ceil(S / CH) rounds (CH sized to stay inside the register budget the j loop sets).
+        {
+            constexpr int CH = (R <= 2) ? 4 : (R <= 4) ? 3 : 2;
+            const float4 *src[R];
+            bool live[R];
 #pragma unroll
-        for (int k = 0; k < R2; ++k) {
-            const int ip = pair_base + k * THREADS;
-            if (2 * ip < p.i_count) {
+            for (int b = 0; b < R; ++b) {
+                const int ip = pair_base + (b >> 1) * THREADS;
+                live[b] = 2 * ip < p.i_count;
+                const int body = live[b] ? 2 * ip + (b & 1) - tb0 : 0;
+                src[b] = p.part + body;
+                fx[b] = fy[b] = fz[b] = 0.f;
+            }
+            for (int s0 = 0; s0 < contributors; s0 += CH) {
+                float4 v[CH][R];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float sx = 0.f, sy = 0.f, sz = 0.f;
-#pragma unroll 8                                       // batch the L2 loads; the adds stay in split order
-                    for (int s = 0; s < contributors; ++s) {
-                        const float4 v = __ldcg(&p.part[(size_t)s * p.split_bodies + (2 * ip + h - tb0)]);
-                        sx += v.x; sy += v.y; sz += v.z;
-                    }
-                    fx[2 * k + h] = sx; fy[2 * k + h] = sy; fz[2 * k + h] = sz;
+                for (int c = 0; c < CH; ++c)
+#pragma unroll
+                    for (int b = 0; b < R; ++b)
+                        v[c][b] = (s0 + c < contributors && live[b]) ? __ldcg(src[b] + (size_t)(s0 + c) * p.split_bodies)
+                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+#pragma unroll
+                    for (int b = 0; b < R; ++b) { fx[b] += v[c][b].x; fy[b] += v[c][b].y; fz[b] += v[c][b].z; }
+            }
+        }
+        if (p.discard_partials) {
+            // The partials of this tile are dead now.  Large split tails (N = 1 M: 55 MB per step) would still be
+            // written back from L2 to HBM as dirty lines nobody reads again: drop the lines instead
+            // (discard.global.L2 = invalidate without write-back).  Every thread has finished reading first.
+            __syncthreads();
+            constexpr int LINES = BI / 8;                       // 128-byte lines per (tile, split) slab
+            const int first = tile * BI - tb0;                  // first body of this tile inside `part`
+            for (int l = tid; l < contributors * LINES; l += THREADS) {
+                const int s = l / LINES, body = first + (l % LINES) * 8;
+                if (body + 8 <= p.split_bodies) {
+                    const float4 *line = p.part + (size_t)s * p.split_bodies + body;
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(line) : "memory");
                 }
             }
         }
@@ -530,12 +597,18 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         p.pos_out[2 * gp] = r0;
         *reinterpret_cast<float2 *>(&p.pos_out[2 * gp + 1]) = r1;      // Gm0,Gm1 never change
         if (p.p2p) {
-            for (int g = 0; g < p.world; ++g) {
-                if (g == p.rank) continue;
-                float4 *dst = p.peer_pos_out[g];
-                NBX_CHECK(dst != nullptr && dst != p.pos_out);
-                dst[2 * gp] = r0;                                       // NVLink store
-                *reinterpret_cast<float2 *>(&dst[2 * gp + 1]) = r1;
+            if (p.mc_pos_out != nullptr) {
+                // one multicast store per half record: the switch replicates it into every replica
+                multimem_st_v4(&p.mc_pos_out[2 * gp], r0);
+                multimem_st_v2(reinterpret_cast<float2 *>(&p.mc_pos_out[2 * gp + 1]), r1);
+            } else {
+                for (int g = 0; g < p.world; ++g) {
+                    if (g == p.rank) continue;
+                    float4 *dst = p.peer_pos_out[g];
+                    NBX_CHECK(dst != nullptr && dst != p.pos_out);
+                    dst[2 * gp] = r0;                                       // NVLink store
+                    *reinterpret_cast<float2 *>(&dst[2 * gp + 1]) = r1;
+                }
             }
         }
         e += (double)(v0.w * (v0.x * v0.x + v0.y * v0.y + v0.z * v0.z));

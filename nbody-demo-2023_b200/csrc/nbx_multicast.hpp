@@ -1,0 +1,204 @@
+// nbx_multicast.hpp -- NVSwitch multicast (NVLS) mapping of the position replicas.
+//
+// With the P2P exchange the step kernel's epilogue stores every updated record into each peer's
+// replica: world-1 NVLink stores per record.  On an NVSwitch system the switch can replicate a
+// single store to every GPU of a multicast team: the replica is backed by one physical allocation
+// per GPU (cuMemCreate), all of them bound to one multicast object (cuMulticastCreate /
+// cuMulticastBindMem), and the object is mapped a second time into each GPU's address space; a
+// `multimem.st` to that mapping lands in every GPU's copy (SASS: MULTIMEM.ST... / ST with the
+// multimem qualifier).  This file owns the driver-API plumbing (libcuda is dlopen'ed, so a
+// single-GPU user never touches it); the kernel side is two instructions in nbx_kernels.cuh.
+//
+// The reference has nothing comparable: its multi-device exchange is MPI_Bcast of nine arrays per
+// step through host memory (ver5_all/GSimulation.cpp:170-189).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace nbx_mc {
+
+struct Api {
+    void *lib = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
+    CUresult (*DeviceGet)(CUdevice *, int) = nullptr;
+    CUresult (*DeviceGetAttribute)(int *, CUdevice_attribute, CUdevice) = nullptr;
+    CUresult (*MulticastCreate)(CUmemGenericAllocationHandle *, const CUmulticastObjectProp *) = nullptr;
+    CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice) = nullptr;
+    CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long) = nullptr;
+    CUresult (*MulticastUnbind)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t) = nullptr;
+    CUresult (*MulticastGetGranularity)(size_t *, const CUmulticastObjectProp *, CUmulticastGranularity_flags) = nullptr;
+    CUresult (*MemCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+    CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*MemAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+    CUresult (*MemGetAllocationGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*MemExportToShareableHandle)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType) = nullptr;
+};
+
+inline Api &api()
+{
+    static Api a;
+    return a;
+}
+
+// Empty string on success, else why the driver API is unusable here.
+inline std::string load()
+{
+    Api &a = api();
+    if (a.lib) return "";
+    void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return std::string("cannot dlopen libcuda.so.1: ") + dlerror();
+    struct Sym { void **slot; const char *name; };
+    const Sym syms[] = {
+        {(void **)&a.GetErrorString, "cuGetErrorString"},
+        {(void **)&a.DeviceGet, "cuDeviceGet"},
+        {(void **)&a.DeviceGetAttribute, "cuDeviceGetAttribute"},
+        {(void **)&a.MulticastCreate, "cuMulticastCreate"},
+        {(void **)&a.MulticastAddDevice, "cuMulticastAddDevice"},
+        {(void **)&a.MulticastBindMem, "cuMulticastBindMem"},
+        {(void **)&a.MulticastUnbind, "cuMulticastUnbind"},
+        {(void **)&a.MulticastGetGranularity, "cuMulticastGetGranularity"},
+        {(void **)&a.MemCreate, "cuMemCreate"},
+        {(void **)&a.MemRelease, "cuMemRelease"},
+        {(void **)&a.MemAddressReserve, "cuMemAddressReserve"},
+        {(void **)&a.MemAddressFree, "cuMemAddressFree"},
+        {(void **)&a.MemMap, "cuMemMap"},
+        {(void **)&a.MemUnmap, "cuMemUnmap"},
+        {(void **)&a.MemSetAccess, "cuMemSetAccess"},
+        {(void **)&a.MemGetAllocationGranularity, "cuMemGetAllocationGranularity"},
+        {(void **)&a.MemExportToShareableHandle, "cuMemExportToShareableHandle"},
+        {(void **)&a.MemImportFromShareableHandle, "cuMemImportFromShareableHandle"},
+    };
+    for (const Sym &s : syms) {
+        *s.slot = dlsym(h, s.name);
+        if (!*s.slot) return std::string("libcuda lacks ") + s.name;
+    }
+    a.lib = h;
+    return "";
+}
+
+inline std::string err(const char *what, CUresult r)
+{
+    const char *s = nullptr;
+    if (api().GetErrorString) api().GetErrorString(r, &s);
+    return std::string(what) + " -> " + (s ? s : "unknown CUDA driver error");
+}
+
+// One GPU's share of one multicast-mapped replica.
+struct Buffer {
+    CUmemGenericAllocationHandle mem = 0;   // this GPU's physical memory
+    CUmemGenericAllocationHandle mc = 0;    // the team's multicast object (same value on every member of a process)
+    CUdeviceptr uc = 0;                     // ordinary (unicast) mapping of `mem`: what the kernels read
+    CUdeviceptr mcva = 0;                   // mapping of the multicast object: multimem.st target
+    size_t size = 0;
+    int device = -1;
+    bool bound = false, owner = false;
+};
+
+inline void release(Buffer &b)
+{
+    Api &a = api();
+    if (!a.lib) return;
+    if (b.device >= 0) cudaSetDevice(b.device);
+    if (b.mcva) { a.MemUnmap(b.mcva, b.size); a.MemAddressFree(b.mcva, b.size); b.mcva = 0; }
+    if (b.bound) {
+        CUdevice dev;
+        if (a.DeviceGet(&dev, b.device) == CUDA_SUCCESS) a.MulticastUnbind(b.mc, dev, 0, b.size);
+        b.bound = false;
+    }
+    if (b.uc) { a.MemUnmap(b.uc, b.size); a.MemAddressFree(b.uc, b.size); b.uc = 0; }
+    if (b.mem) { a.MemRelease(b.mem); b.mem = 0; }
+    if (b.mc && b.owner) a.MemRelease(b.mc);
+    b.mc = 0;
+}
+
+// Team set-up inside ONE process: `devices` = CUDA ordinals of the members, in rank order.
+// On success bufs[g] holds member g's mappings of a `bytes`-sized replica (contents undefined).
+// Returns "" or the reason multicast is unavailable (everything already created is released).
+inline std::string create_team(const std::vector<int> &devices, size_t bytes, std::vector<Buffer> &bufs)
+{
+    std::string why = load();
+    if (!why.empty()) return why;
+    Api &a = api();
+    const int G = (int)devices.size();
+    bufs.assign((size_t)G, Buffer());
+    std::vector<CUdevice> cudev((size_t)G);
+    for (int g = 0; g < G; ++g) {
+        cudaSetDevice(devices[g]);
+        cudaFree(0);                                   // make sure the primary context exists
+        CUresult r = a.DeviceGet(&cudev[g], devices[g]);
+        if (r != CUDA_SUCCESS) return err("cuDeviceGet", r);
+        int ok = 0;
+        r = a.DeviceGetAttribute(&ok, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, cudev[g]);
+        if (r != CUDA_SUCCESS || !ok) return "device " + std::to_string(devices[g]) + " does not support NVSwitch multicast";
+    }
+    CUmulticastObjectProp mp = {};
+    mp.numDevices = (unsigned)G;
+    mp.handleTypes = 0;
+    mp.flags = 0;
+    mp.size = bytes;
+    size_t gran = 0;
+    CUresult r = a.MulticastGetGranularity(&gran, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED);
+    if (r != CUDA_SUCCESS || gran == 0) return err("cuMulticastGetGranularity", r);
+    CUmemAllocationProp ap = {};
+    ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    ap.location.id = devices[0];
+    size_t mgran = 0;
+    r = a.MemGetAllocationGranularity(&mgran, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED);
+    if (r != CUDA_SUCCESS || mgran == 0) return err("cuMemGetAllocationGranularity", r);
+    if (mgran > gran) gran = (mgran + gran - 1) / gran * gran;
+    const size_t size = (bytes + gran - 1) / gran * gran;
+    mp.size = size;
+
+    auto fail_all = [&](const std::string &w) {
+        for (Buffer &b : bufs) release(b);
+        return w;
+    };
+    CUmemGenericAllocationHandle mc = 0;
+    r = a.MulticastCreate(&mc, &mp);
+    if (r != CUDA_SUCCESS) return err("cuMulticastCreate", r);
+    for (int g = 0; g < G; ++g) {
+        bufs[g].mc = mc; bufs[g].size = size; bufs[g].device = devices[g]; bufs[g].owner = (g == 0);
+    }
+    for (int g = 0; g < G; ++g)                        // every member joins before anyone binds
+        if ((r = a.MulticastAddDevice(mc, cudev[g])) != CUDA_SUCCESS) return fail_all(err("cuMulticastAddDevice", r));
+    std::vector<CUmemAccessDesc> everyone((size_t)G);
+    for (int g = 0; g < G; ++g) {
+        everyone[g].location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        everyone[g].location.id = devices[g];
+        everyone[g].flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    }
+    for (int g = 0; g < G; ++g) {
+        Buffer &b = bufs[g];
+        cudaSetDevice(devices[g]);
+        ap.location.id = devices[g];
+        if ((r = a.MemCreate(&b.mem, size, &ap, 0)) != CUDA_SUCCESS) return fail_all(err("cuMemCreate", r));
+        if ((r = a.MulticastBindMem(mc, 0, b.mem, 0, size, 0)) != CUDA_SUCCESS) return fail_all(err("cuMulticastBindMem", r));
+        b.bound = true;
+        if ((r = a.MemAddressReserve(&b.uc, size, gran, 0, 0)) != CUDA_SUCCESS) return fail_all(err("cuMemAddressReserve", r));
+        if ((r = a.MemMap(b.uc, size, 0, b.mem, 0)) != CUDA_SUCCESS) return fail_all(err("cuMemMap(unicast)", r));
+        // every member may also address this copy directly (the unicast P2P path stays usable)
+        if ((r = a.MemSetAccess(b.uc, size, everyone.data(), (size_t)G)) != CUDA_SUCCESS) return fail_all(err("cuMemSetAccess(unicast)", r));
+    }
+    for (int g = 0; g < G; ++g) {
+        Buffer &b = bufs[g];
+        cudaSetDevice(devices[g]);
+        if ((r = a.MemAddressReserve(&b.mcva, size, gran, 0, 0)) != CUDA_SUCCESS) return fail_all(err("cuMemAddressReserve(mc)", r));
+        if ((r = a.MemMap(b.mcva, size, 0, mc, 0)) != CUDA_SUCCESS) return fail_all(err("cuMemMap(multicast)", r));
+        if ((r = a.MemSetAccess(b.mcva, size, &everyone[g], 1)) != CUDA_SUCCESS) return fail_all(err("cuMemSetAccess(multicast)", r));
+    }
+    return "";
+}
+
+}  // namespace nbx_mc

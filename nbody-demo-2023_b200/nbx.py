@@ -48,7 +48,7 @@ class Info(C.Structure):
         "i_tiles", "whole_tiles", "j_splits", "ctas_per_sm", "use_graph", "exchange", "variant")] + [
         ("kernel_launches", C.c_longlong), ("aux_launches", C.c_longlong),
         ("last_run_seconds", C.c_double), ("kernel_seconds_total", C.c_double),
-        ("device_error", C.c_int), ("peer_timeout_ms", C.c_int)]
+        ("device_error", C.c_int), ("peer_timeout_ms", C.c_int), ("multicast", C.c_int), ("reserved", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -50,6 +50,8 @@ def lib() -> C.CDLL:
         L.oracle_acc_fp64.restype = None
         L.oracle_acc_f32.argtypes = [C.c_int] + [_f32p] * 4 + [C.c_int, _i32p] + [_f32p] * 3
         L.oracle_acc_f32.restype = None
+        L.oracle_run_fp64.argtypes = [C.c_int] + [_f64p] * 6 + [_f32p, C.c_double, C.c_int, _f64p]
+        L.oracle_run_fp64.restype = C.c_int
         L.oracle_kenergy_fp64.argtypes = [C.c_int] + [_f32p] * 4
         L.oracle_kenergy_fp64.restype = C.c_double
         L.oracle_gflop_per_step.argtypes = [C.c_int]
@@ -99,6 +101,16 @@ def run(state: State, nsteps: int, dt: float = 0.1, variant: str = "ver2") -> np
     if rc != 0:
         raise MemoryError("oracle allocation failed")
     return ke[:nsteps]
+
+
+def run_fp64(state: State, nsteps: int, dt: float = float(np.float32(0.1))):
+    """fp64 "truth" run from `state` (float inputs widened): returns (pos float64[n,3], vel float64[n,3],
+    kenergy float64[nsteps]).  dt defaults to the float value 0.1f the reference uses."""
+    p = [np.ascontiguousarray(getattr(state, f), dtype=np.float64) for f in ("px", "py", "pz", "vx", "vy", "vz")]
+    ke = np.zeros(max(nsteps, 1), dtype=np.float64)
+    if lib().oracle_run_fp64(state.n, *p, np.ascontiguousarray(state.mass, dtype=np.float32), float(dt), nsteps, ke) != 0:
+        raise MemoryError("oracle allocation failed")
+    return np.stack(p[:3], axis=1), np.stack(p[3:], axis=1), ke[:nsteps]
 
 
 def acc_fp64(state: State, sel: np.ndarray) -> np.ndarray:

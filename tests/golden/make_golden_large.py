@@ -2,7 +2,7 @@
 """Known-answer fixtures at the HEADLINE sizes, generated from the UNMODIFIED reference (ver8, its
 fastest CPU version: ver8/GSimulation.cpp:142-215) compiled by oracle/Makefile into oracle/_ref/.
 
-    python tests/golden/make_golden_large.py [n262144] [c2] [c3] [c1]      (default: all)
+    python tests/golden/make_golden_large.py [n262144] [c2] [c3] [c1] [c1s10]      (default: all)
 
   n262144  N =   262,144 uniform cube, 10 steps   (~1 min on 8 cores)
   c2       N = 1,048,576 uniform cube,  2 steps   (~3 min)            BASELINE config 2
@@ -33,6 +33,7 @@ CASES = {
     "c2": dict(n=1 << 20, steps=2, ic="uniform"),
     "c3": dict(n=1 << 22, steps=1, ic="plummer"),
     "c1": dict(n=16384, steps=500, ic="uniform"),
+    "c1s10": dict(n=16384, steps=10, ic="uniform"),        # the same run after 10 steps (the north star's position gate)
 }
 NSEL = 4096
 

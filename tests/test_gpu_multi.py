@@ -160,11 +160,13 @@ torch.distributed.destroy_process_group()
 def test_default_plan_multi_gpu_vs_reference_fixture(nbx, world, name):
     """i-sharded runs with the plan nbx_run picks by itself (at C2 on 2 GPUs and C3 on 8 GPUs: 444 unsplit
     tiles + 68 split 37 ways per GPU; default P2P exchange) against ver8's kinetic energies and sampled
-    positions (tests/golden/large_*_ver8.npz): the north star's 1e-4 gates."""
-    from test_gpu_headline import check_against_fixture, load
+    positions (tests/golden/large_*_ver8.npz) and the fp64 truth (truth_*_fp64.npz): the gates of
+    tests/test_gpu_headline.py."""
+    from test_gpu_headline import check_against_fixtures, load
     if _ngpu(nbx) < world:
         pytest.skip(f"needs {world} GPUs")
     fx = load(name)
+    truth = load(name, "truth", "fp64")
     n, steps = int(fx["n"]), int(fx["steps"])
     arrs = nbx.ic(n, str(fx["ic"]))
     ctxs = [nbx.Context(n, device=g, rank=g, world=world) for g in range(world)]
@@ -178,7 +180,7 @@ def test_default_plan_multi_gpu_vs_reference_fixture(nbx, world, name):
         out = [np.zeros(n, dtype=np.float32) for _ in range(6)]
         for c in ctxs:
             c.download_shard(*out)          # every rank contributes its own slice of all six arrays
-        check_against_fixture(fx, ke, out, f"{name} on {world} GPUs, default plan")
+        check_against_fixtures(fx, truth, ke, out, f"{name} on {world} GPUs, default plan")
         ref = ctxs[0].state()
         for c in ctxs[1:]:                  # replicas agree bit for bit
             for a, b in zip(c.state()[:3], ref[:3]):
