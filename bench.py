@@ -518,6 +518,28 @@ def main():
             finally:
                 c2.close()
 
+        # NVSwitch multicast needs ONE process driving all the GPUs (the multicast handle is not exported across
+        # processes): rank 0 runs the same workload through nbx_run_group while the other ranks wait on a CPU barrier
+        gloo = torch.distributed.new_group(backend="gloo")
+        if rank == 0:
+            try:
+                ctxs = [nbx.Context(n, device=g, rank=g, world=world) for g in range(world)]
+                try:
+                    nbx.p2p_attach_group(ctxs)
+                    nbx.upload_group(ctxs, *host)
+                    nbx.run_group(ctxs, 1)
+                    ks = sum(nbx.run_group(ctxs, 1)[1] for _ in range(2))
+                    exchange_ab["p2p_one_process"] = {"ms_per_step": round(1e3 * ks / 2, 3), "value": round(pairs_per_step * 2 / ks / 1e9, 1),
+                                                      "multicast": bool(ctxs[0].info()["multicast"]),
+                                                      "what": "nbx_run_group from rank 0's process over all GPUs; multicast = the epilogue exchange is one "
+                                                              "multimem.st per record through a cuMulticast mapping instead of world-1 NVLink stores"}
+                finally:
+                    for c in ctxs:
+                        c.close()
+            except Exception as ex:
+                exchange_ab["p2p_one_process"] = {"error": repr(ex)}
+        torch.distributed.barrier(group=gloo)
+
     # ---- strong-scaling anchor: T1 on C3 (measured by the 1-GPU run; re-used by N > 1 runs on the same box)
     strong = None
     also = {}

@@ -210,6 +210,10 @@ NBX_API int nbx_comm_init_all(nbx_ctx **ctxs, int count);
 NBX_API int nbx_run_group(nbx_ctx **ctxs, int count, int nsteps, double *kenergy_out, double *seconds_out);
 NBX_API int nbx_p2p_export(nbx_ctx *ctx, void *blob_out);
 NBX_API int nbx_p2p_attach(nbx_ctx *ctx, const void *blobs /* world * NBX_P2P_BLOB_BYTES */);
+/* One process: export + attach for every context of the group in one call, after trying to put the
+ * replicas behind an NVSwitch multicast team (option "multicast").  What nbx_run_group does by itself;
+ * public so that a host can see the failure and choose the NCCL exchange instead. */
+NBX_API int nbx_p2p_attach_group(nbx_ctx **ctxs, int count);
 
 /* ---- host helpers ------------------------------------------------------------------
  * Initial conditions with the reference's own RNG call sequence

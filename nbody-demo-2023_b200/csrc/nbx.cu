@@ -1072,6 +1072,14 @@ static int attach_group(nbx_ctx **ctxs, int count)
     return NBX_OK;
 }
 
+int nbx_p2p_attach_group(nbx_ctx **ctxs, int count)
+{
+    if (!ctxs || count < 1 || count > nbx::kMaxWorld) return fail(NBX_ERR_ARG, "bad context array");
+    for (int g = 0; g < count; ++g)
+        if (!ctxs[g] || ctxs[g]->world != count || ctxs[g]->rank != g) return fail(NBX_ERR_ARG, "ctxs[%d] is not rank %d of %d", g, g, count);
+    return count > 1 ? attach_group(ctxs, count) : NBX_OK;
+}
+
 int nbx_run_group(nbx_ctx **ctxs, int count, int nsteps, double *kenergy_out, double *seconds_out)
 {
     if (!ctxs || count < 1) return fail(NBX_ERR_ARG, "bad context array");
@@ -1291,8 +1299,12 @@ int nbx_p2p_export(nbx_ctx *c, void *blob_out)
     // platform without CUDA IPC can still run the one-process group
     b.pad = 1;
     void *bufs[3] = {c->pos[0], c->pos[1], c->flags};
-    for (int k = 0; k < 3; ++k)
-        if (cudaIpcGetMemHandle(&b.h[k], bufs[k]) != cudaSuccess) { cudaGetLastError(); b.pad = 0; }
+    if (c->mc_active) {
+        b.pad = 0;       // multicast-bound replicas are driver-API (cuMemCreate) memory: legacy CUDA IPC does not apply
+    } else {
+        for (int k = 0; k < 3; ++k)
+            if (cudaIpcGetMemHandle(&b.h[k], bufs[k]) != cudaSuccess) { cudaGetLastError(); b.pad = 0; }
+    }
     std::memset(blob_out, 0, NBX_P2P_BLOB_BYTES);
     std::memcpy(blob_out, &b, sizeof b);
     return NBX_OK;

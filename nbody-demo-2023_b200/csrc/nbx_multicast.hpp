@@ -5,8 +5,8 @@
 // single store to every GPU of a multicast team: the replica is backed by one physical allocation
 // per GPU (cuMemCreate), all of them bound to one multicast object (cuMulticastCreate /
 // cuMulticastBindMem), and the object is mapped a second time into each GPU's address space; a
-// `multimem.st` to that mapping lands in every GPU's copy (SASS: MULTIMEM.ST... / ST with the
-// multimem qualifier).  This file owns the driver-API plumbing (libcuda is dlopen'ed, so a
+// `multimem.st` to that mapping lands in every GPU's copy (on sm_100a ptxas lowers multimem.st to an
+// ordinary STG.E.128.STRONG.SYS -- the replication is a property of the mapping, not of the opcode).  This file owns the driver-API plumbing (libcuda is dlopen'ed, so a
 // single-GPU user never touches it); the kernel side is two instructions in nbx_kernels.cuh.
 //
 // The reference has nothing comparable: its multi-device exchange is MPI_Bcast of nine arrays per
@@ -102,7 +102,8 @@ struct Buffer {
     CUdeviceptr mcva = 0;                   // mapping of the multicast object: multimem.st target
     size_t size = 0;
     int device = -1;
-    bool bound = false, owner = false;
+    bool bound = false;
+    int *team_refs = nullptr;               // members still holding `mc`; the last one to leave releases the object
 };
 
 inline void release(Buffer &b)
@@ -118,8 +119,15 @@ inline void release(Buffer &b)
     }
     if (b.uc) { a.MemUnmap(b.uc, b.size); a.MemAddressFree(b.uc, b.size); b.uc = 0; }
     if (b.mem) { a.MemRelease(b.mem); b.mem = 0; }
-    if (b.mc && b.owner) a.MemRelease(b.mc);
+    // the multicast object outlives every member's binding and mapping: the last member out frees it.
+    // (Never hand these addresses to legacy CUDA IPC: cudaIpcGetMemHandle on a multicast-bound mapping made
+    // a later cuMulticastUnbind crash inside the driver -- nbx_p2p_export skips it for such replicas.)
+    if (b.mc && b.team_refs && --*b.team_refs == 0) {
+        a.MemRelease(b.mc);
+        delete b.team_refs;
+    }
     b.mc = 0;
+    b.team_refs = nullptr;
 }
 
 // Team set-up inside ONE process: `devices` = CUDA ordinals of the members, in rank order.
@@ -168,8 +176,9 @@ inline std::string create_team(const std::vector<int> &devices, size_t bytes, st
     CUmemGenericAllocationHandle mc = 0;
     r = a.MulticastCreate(&mc, &mp);
     if (r != CUDA_SUCCESS) return err("cuMulticastCreate", r);
+    int *refs = new int(G);
     for (int g = 0; g < G; ++g) {
-        bufs[g].mc = mc; bufs[g].size = size; bufs[g].device = devices[g]; bufs[g].owner = (g == 0);
+        bufs[g].mc = mc; bufs[g].size = size; bufs[g].device = devices[g]; bufs[g].team_refs = refs;
     }
     for (int g = 0; g < G; ++g)                        // every member joins before anyone binds
         if ((r = a.MulticastAddDevice(mc, cudev[g])) != CUDA_SUCCESS) return fail_all(err("cuMulticastAddDevice", r));

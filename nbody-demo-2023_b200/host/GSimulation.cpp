@@ -26,6 +26,8 @@
 #include <iomanip>
 #include <iostream>
 
+#include <unistd.h>
+
 #include "cpu_time.hpp"
 #include "ic.hpp"
 #include "nbx.h"
@@ -150,20 +152,28 @@ void GSimulation::start()
         if (std::getenv("NBODY_PEER_TIMEOUT_MS") && nbx_set_option(ctx[g], "peer_timeout_ms", env_int("NBODY_PEER_TIMEOUT_MS", 30000))) die("peer_timeout_ms");
     }
     if (G > 1 && exchange == NBX_EXCHANGE_P2P) {
-        // map every GPU's replica into every other GPU; if some pair has no peer access, take the
-        // NCCL all-gather on all GPUs instead (both are GPU paths)
-        std::vector<unsigned char> blobs((size_t)G * NBX_P2P_BLOB_BYTES);
-        bool ok = true;
-        for (int g = 0; g < G && ok; ++g) ok = nbx_p2p_export(ctx[g], blobs.data() + (size_t)g * NBX_P2P_BLOB_BYTES) == NBX_OK;
-        for (int g = 0; g < G && ok; ++g) ok = nbx_p2p_attach(ctx[g], blobs.data()) == NBX_OK;
-        if (!ok) {
+        // map every GPU's replica into every other GPU (through an NVSwitch multicast team where the driver
+        // offers one); if some pair has no peer access, take the NCCL all-gather on all GPUs instead
+        // (both are GPU paths)
+        if (nbx_p2p_attach_group(ctx.data(), G)) {
             std::cerr << "nbody.x: P2P exchange unavailable (" << nbx_last_error() << "); using the NCCL all-gather" << std::endl;
             exchange = NBX_EXCHANGE_NCCL;
         }
     }
     for (int g = 0; g < G; ++g)
         if (nbx_set_option(ctx[g], "exchange", exchange)) die("exchange");
-    if (G > 1 && exchange != NBX_EXCHANGE_P2P && nbx_comm_init_all(ctx.data(), G)) die("nbx_comm_init_all");
+    if (G > 1 && exchange != NBX_EXCHANGE_P2P) {
+        // NCCL_DEBUG=VERSION makes NCCL print its version line to stdout whatever NCCL_DEBUG_FILE says: point
+        // fd 1 at stderr while the communicators are created so the table stays byte-compatible
+        std::cout.flush();
+        std::fflush(stdout);
+        const int saved = dup(1);
+        if (saved >= 0) dup2(2, 1);
+        const int rc = nbx_comm_init_all(ctx.data(), G);
+        std::fflush(stdout);
+        if (saved >= 0) { dup2(saved, 1); close(saved); }
+        if (rc) die("nbx_comm_init_all");
+    }
     // each GPU takes its own shard over PCIe; the packed records go GPU to GPU
     if (nbx_upload_group(ctx.data(), G, particles->pos_x.data(), particles->pos_y.data(), particles->pos_z.data(),
                          particles->vel_x.data(), particles->vel_y.data(), particles->vel_z.data(), particles->mass.data()))

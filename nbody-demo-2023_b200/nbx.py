@@ -30,7 +30,7 @@ SYMBOLS = [
     "nbx_abi_version", "nbx_last_error", "nbx_device_count", "nbx_create", "nbx_destroy",
     "nbx_set_option", "nbx_get_info", "nbx_plan", "nbx_trace_read", "nbx_variant_count", "nbx_variant_name", "nbx_upload",
     "nbx_download", "nbx_upload_sharded", "nbx_upload_group", "nbx_download_shard", "nbx_run", "nbx_accelerations", "nbx_simulate", "nbx_comm_unique_id",
-    "nbx_comm_init", "nbx_comm_init_all", "nbx_run_group", "nbx_p2p_export", "nbx_p2p_attach",
+    "nbx_comm_init", "nbx_comm_init_all", "nbx_run_group", "nbx_p2p_export", "nbx_p2p_attach", "nbx_p2p_attach_group",
     "nbx_ic_uniform", "nbx_ic_plummer", "nbx_gflop_per_step", "nbx_host_alloc", "nbx_host_free",
 ]
 
@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
         L.nbx_run_group.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, _f64p, _f64p]
         L.nbx_p2p_export.argtypes = [C.c_void_p, C.c_void_p]
         L.nbx_p2p_attach.argtypes = [C.c_void_p, C.c_void_p]
+        L.nbx_p2p_attach_group.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.nbx_ic_uniform.argtypes = [C.c_int] + [_f32p] * 7
         L.nbx_ic_uniform.restype = None
         L.nbx_ic_plummer.argtypes = [C.c_int] + [_f32p] * 7
@@ -251,6 +252,11 @@ def comm_unique_id() -> bytes:
 def comm_init_all(ctxs):
     arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
     _check(lib().nbx_comm_init_all(arr, len(ctxs)))
+
+
+def p2p_attach_group(ctxs):
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    _check(lib().nbx_p2p_attach_group(arr, len(ctxs)))
 
 
 def upload_group(ctxs, px, py, pz, vx, vy, vz, mass):

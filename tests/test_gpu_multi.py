@@ -251,3 +251,49 @@ def test_sharded_upload_equals_full_upload(nbx):
     finally:
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_multicast_exchange_equals_unicast(nbx, world):
+    """NVSwitch multicast (one multimem.st per record, cuMulticast* mapping) against the unicast NVLink stores:
+    same bits.  Where the driver offers no multicast the library says why (NBX_VERBOSE) and the test
+    only checks that the request `multicast=1` fails cleanly."""
+    if _ngpu(nbx) < world:
+        pytest.skip(f"needs {world} GPUs")
+    n, steps = 40960, 5
+    arrs = nbx.ic(n)
+    res = {}
+    for mode in (0, -1):
+        ctxs = [nbx.Context(n, device=g, rank=g, world=world) for g in range(world)]
+        try:
+            for c in ctxs:
+                c.set_option("multicast", mode)
+            nbx.p2p_attach_group(ctxs)
+            nbx.upload_group(ctxs, *arrs)
+            ke, _ = nbx.run_group(ctxs, steps)
+            out = [np.zeros(n, dtype=np.float32) for _ in range(6)]
+            for c in ctxs:
+                c.download_shard(*out)
+            res[mode] = (ke, out, ctxs[0].info()["multicast"], [c.state()[:3] for c in ctxs])
+        finally:
+            for c in ctxs:
+                c.close()
+    assert res[0][2] == 0
+    print(f"\nmulticast active on {world} GPUs: {bool(res[-1][2])}")
+    assert np.array_equal(res[0][0], res[-1][0])
+    for a, b in zip(res[0][1], res[-1][1]):
+        assert np.array_equal(a, b)
+    for rep in res[-1][3][1:]:                       # every replica received every store
+        for a, b in zip(rep, res[-1][3][0]):
+            assert np.array_equal(a, b)
+    if not res[-1][2]:
+        ctxs = [nbx.Context(n, device=g, rank=g, world=world) for g in range(world)]
+        try:
+            for c in ctxs:
+                c.set_option("multicast", 1)
+            with pytest.raises(nbx.NbxError) as e:
+                nbx.p2p_attach_group(ctxs)
+            assert "multicast" in str(e.value)
+        finally:
+            for c in ctxs:
+                c.close()
