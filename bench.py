@@ -231,9 +231,9 @@ class Bench:
             self.host_cache = {key: host}          # keep one workload's buffers at a time
         return self.host_cache[key]
 
-    def make_ctx(self, key, exchange=None, variant=-1, j_splits=0):
+    def make_ctx(self, key, exchange=None, variant=-1, j_splits=0, multicast=-1):
         nbx = self.nbx
-        ctx = self.dist.make_sharded_context(nbx, WORKLOADS[key]["n"], exchange, device=self.local_rank)
+        ctx = self.dist.make_sharded_context(nbx, WORKLOADS[key]["n"], exchange, device=self.local_rank, multicast=multicast)
         if variant >= 0:
             ctx.set_option("variant", variant)
         if j_splits > 0:
@@ -460,6 +460,7 @@ def main():
     out = [nbx.pinned_empty(n) for _ in range(6)]
     exchange = {"p2p": nbx.EXCHANGE_P2P, "nccl": nbx.EXCHANGE_NCCL, "nccl_overlap": nbx.EXCHANGE_NCCL_OVERLAP}[args.exchange]
     ctx = B.make_ctx(wl_key, exchange, args.variant, args.j_splits)
+    exchange_used, multicast_used = (ctx.exchange_used if world > 1 else exchange), ctx.multicast
     B.upload(ctx, host)
     B.sm_count = ctx.info()["sm_count"]
 
@@ -508,13 +509,14 @@ def main():
     if world > 1 and not args.no_extras:
         exchange_ab = {}
         ctx.close(); ctx = None
-        for name, mode in (("nccl", nbx.EXCHANGE_NCCL), ("nccl_overlap", nbx.EXCHANGE_NCCL_OVERLAP), ("p2p", nbx.EXCHANGE_P2P)):
-            c2 = B.make_ctx(wl_key, mode)
+        for name, mode in (("nccl", nbx.EXCHANGE_NCCL), ("nccl_overlap", nbx.EXCHANGE_NCCL_OVERLAP), ("p2p", nbx.EXCHANGE_P2P),
+                           ("p2p_unicast", nbx.EXCHANGE_P2P)):
+            c2 = B.make_ctx(wl_key, mode, multicast=0 if name == "p2p_unicast" else -1)
             try:
                 B.upload(c2, host)
                 ks, _, _ = B.timed_steps(c2, 2, 1)
                 exchange_ab[name] = {"ms_per_step": round(1e3 * ks / 2, 3), "value": round(pairs_per_step * 2 / ks / 1e9, 1),
-                                     "used": XCH_NAMES[c2.exchange_used]}
+                                     "used": XCH_NAMES[c2.exchange_used], "multicast": c2.multicast}
             finally:
                 c2.close()
 
@@ -546,7 +548,10 @@ def main():
     if not args.no_extras:
         if ctx is not None:
             ctx.close(); ctx = None
-        box = socket.gethostname()
+        try:       # the anchor is only valid for the GPU it was measured on (boxes share a hostname, GPUs differ by ~1.5 %)
+            box = socket.gethostname() + "/" + str(torch.cuda.get_device_properties(0).uuid)
+        except Exception:
+            box = socket.gethostname()
         if world == 1:
             blk = B.side_workload("c3", 3, 1)
             strong = {"workload": WORKLOADS["c3"]["name"], "ms_per_step": blk["ms_per_step"], "value": blk["value"], "steps": 3,
@@ -612,7 +617,7 @@ def main():
         "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "n_bodies": n, "pairs_per_step": pairs_per_step,
-                   "parallelism": f"i-shard x{args.gpus}" + (f", exchange={XCH_NAMES[exchange]}" if args.gpus > 1 else ""),
+                   "parallelism": f"i-shard x{args.gpus}" + (f", exchange={XCH_NAMES[exchange_used]}" + (" through NVSwitch multicast (one multimem.st per record)" if multicast_used else "") if args.gpus > 1 else ""),
                    "kernel_shape": nbx.variant_names()[info1["variant"]],
                    "i_tiles": info1["i_tiles"], "whole_tiles": info1["whole_tiles"], "j_splits": info1["j_splits"], "ctas_per_sm": info1["ctas_per_sm"],
                    "l2": "flushed between timed steps (256 MiB memset); positions (16 B/body) are L2-resident by design within a step",

@@ -112,9 +112,10 @@ NBX_API void nbx_destroy(nbx_ctx *ctx);
  *   "graph"     1/0 replay steps from a CUDA graph (auto: on for small N)
  *   "accurate"  1/0 two-level accumulation (float per j tile, then double): large-N accuracy option
  *   "pdl"       1/0 programmatic dependent launch between consecutive steps (-1 = auto: many-wave grids only)
- *   "multicast" P2P exchange inside one process (nbx_run_group): -1 auto = use NVSwitch multicast
- *               (cuMulticast* + multimem.st) when the driver offers it, 0 never, 1 fail if unavailable;
- *               NBX_VERBOSE=1 prints why it was not used
+ *   "multicast" P2P exchange: -1 auto = use NVSwitch multicast (cuMulticast* + multimem.st) when the driver
+ *               offers it, 0 never, 1 fail if unavailable; NBX_VERBOSE=1 prints why it was not used.  Works inside
+ *               one process (nbx_run_group / nbx_p2p_attach_group) and across processes (nbx_p2p_attach, when a
+ *               communicator exists: the set-up is collective and must be called with the same option on every rank)
  *   "smem_pad_kb"  extra dynamic shared memory per CTA in KiB (tuning: caps the resident CTAs per SM)
  *   "exchange"  NBX_EXCHANGE_* (default NBX_EXCHANGE_P2P)
  *   "peer_timeout_ms"  P2P exchange: how long a step may wait inside the kernel for a peer GPU to

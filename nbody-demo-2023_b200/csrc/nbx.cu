@@ -217,6 +217,7 @@ struct nbx_ctx {
     nbx_mc::Buffer mcbuf[2];                     // NVSwitch multicast mappings of pos[0], pos[1] (when mc_active)
     bool mc_active = false;
     std::string mc_note = "not attempted";
+    float4 *retired_pos[2] = {nullptr, nullptr};   // cudaMalloc replicas superseded by multicast memory while peers hold IPC mappings of them
     int opt_multicast = -1;                      // -1 auto (try it inside one process), 0 off, 1 required
 
     long long kernel_launches = 0, aux_launches = 0;
@@ -673,6 +674,7 @@ void nbx_destroy(nbx_ctx *c)
     } else {
         cudaFree(c->pos[0]); cudaFree(c->pos[1]);
     }
+    cudaFree(c->retired_pos[0]); cudaFree(c->retired_pos[1]);
     cudaFree(c->vel); cudaFree(c->part); cudaFree(c->acc);
     cudaFree(c->tile_ticket); cudaFree(c->ke_part); cudaFree(c->counters); cudaFree(c->flags);
     cudaFree(c->ke_dev); cudaFree(c->stage); cudaFree(c->trace);
@@ -1310,11 +1312,61 @@ int nbx_p2p_export(nbx_ctx *c, void *blob_out)
     return NBX_OK;
 }
 
-int nbx_p2p_attach(nbx_ctx *c, const void *blobs)
+// min over the ranks of a small integer (NCCL on the context's stream): the consensus step of collective set-up
+static int consensus_min(nbx_ctx *c, int mine, int *all)
 {
-    if (!c || !blobs) return fail(NBX_ERR_ARG, "NULL argument");
+    int *word = c->counters + 4;
+    CU(cudaMemcpyAsync(word, &mine, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllReduce(word, word, 1, ncclInt, ncclMin, c->comm, c->stream));
+    CU(cudaMemcpyAsync(all, word, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return NBX_OK;
+}
+
+// One process per GPU: put the replicas behind an NVSwitch multicast team shared ACROSS the processes
+// (nbx_multicast.hpp, second half).  Collective over the communicator; every phase ends in a consensus so that
+// either all ranks switch to the multicast stores or none does.  Unavailable is not an error (unless "multicast" = 1).
+static int try_multicast_procs(nbx_ctx *c, long long pid0, const void *tag0)
+{
+    if (c->opt_multicast == 0 || c->mc_active || !c->comm) return NBX_OK;
+    char name[96];
+    std::snprintf(name, sizeof name, "nbx-mc-%lld-%p", pid0, tag0);
+    const size_t bytes = (size_t)c->n_pad * sizeof(float4);
+    nbx_mc::Buffer bufs[2];
+    std::string why;
+    int all = 0, rc;
+    auto give_up = [&](const std::string &w) {
+        nbx_mc::release(bufs[0]); nbx_mc::release(bufs[1]);
+        cudaGetLastError();
+        c->mc_note = w;
+        if (c->opt_multicast == 1) return fail(NBX_ERR_CUDA, "NVSwitch multicast required but unavailable: %s", w.c_str());
+        if (std::getenv("NBX_VERBOSE"))
+            std::fprintf(stderr, "nbx: rank %d: NVSwitch multicast unavailable (%s); the exchange uses unicast NVLink stores\n", c->rank, w.c_str());
+        return (int)NBX_OK;
+    };
+    const char *phase[3] = {"open", "join", "bind"};
+    for (int ph = 0; ph < 3; ++ph) {
+        why = ph == 0 ? nbx_mc::mp_open_team(c->rank, c->world, c->device, bytes, name, bufs, 2)
+              : ph == 1 ? nbx_mc::mp_join(bufs, 2) : nbx_mc::mp_bind_and_map(bufs, 2);
+        if ((rc = consensus_min(c, why.empty() ? 1 : 0, &all))) { give_up("consensus failed"); return rc; }
+        if (!all) return give_up(why.empty() ? std::string("another rank failed in phase ") + phase[ph] : why);
+    }
     CU(cudaSetDevice(c->device));
-    const unsigned char *base = static_cast<const unsigned char *>(blobs);
+    for (int b = 0; b < 2; ++b) {
+        float4 *fresh = reinterpret_cast<float4 *>(bufs[b].uc);
+        CU(cudaMemcpy(fresh, c->pos[b], bytes, cudaMemcpyDeviceToDevice));
+        c->retired_pos[b] = c->pos[b];          // peers hold CUDA IPC mappings of it: free it with the context
+        c->pos[b] = fresh;
+        c->mcbuf[b] = bufs[b];
+    }
+    c->mc_active = true;
+    c->mc_note = "active (across processes)";
+    c->resolved = false;
+    return NBX_OK;
+}
+
+static int map_peers(nbx_ctx *c, const unsigned char *base)
+{
     for (int g = 0; g < c->world; ++g) {
         P2PBlob b;
         std::memcpy(&b, base + (size_t)g * NBX_P2P_BLOB_BYTES, sizeof b);
@@ -1346,6 +1398,32 @@ int nbx_p2p_attach(nbx_ctx *c, const void *blobs)
         c->peer_pos[1][g] = static_cast<float4 *>(ptr[1]);
         c->peer_flags[g] = static_cast<int *>(ptr[2]);
     }
+    return NBX_OK;
+}
+
+int nbx_p2p_attach(nbx_ctx *c, const void *blobs)
+{
+    if (!c || !blobs) return fail(NBX_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const unsigned char *base = static_cast<const unsigned char *>(blobs);
+    const int map_rc = map_peers(c, base);
+    P2PBlob b0, bl;
+    std::memcpy(&b0, base, sizeof b0);
+    std::memcpy(&bl, base + (size_t)(c->world - 1) * NBX_P2P_BLOB_BYTES, sizeof bl);
+    const bool across_processes = c->world > 1 && b0.magic == 0x4e425850u && bl.magic == 0x4e425850u && b0.pid != bl.pid;
+    if (across_processes && c->comm && c->opt_multicast != 0) {
+        // the multicast set-up below is collective: first agree that every rank got this far
+        const std::string why = g_err;
+        int all = 0, rc;
+        if ((rc = consensus_min(c, map_rc == NBX_OK ? 1 : 0, &all))) return rc;
+        if (!all) {
+            if (map_rc) { g_err = why; return map_rc; }
+            return fail(NBX_ERR_CUDA, "another rank could not map its peers' buffers");
+        }
+        c->p2p_ready = true;
+        return try_multicast_procs(c, (long long)b0.pid, b0.raw[0]);
+    }
+    if (map_rc) return map_rc;
     c->p2p_ready = true;
     return NBX_OK;
 }

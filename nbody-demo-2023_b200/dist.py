@@ -77,7 +77,7 @@ def barrier():
         dist.barrier()
 
 
-def make_sharded_context(nbx, n: int, exchange: int | None = None, device: int | None = None, **ctx_kw):
+def make_sharded_context(nbx, n: int, exchange: int | None = None, device: int | None = None, multicast: int = -1, **ctx_kw):
     """Create this rank's nbx.Context (i-shard rank/world) and wire the exchange (default: the
     library's default, P2P): NCCL unique id broadcast from rank 0, and for P2P the all-gather of handle blobs.
     If ANY rank cannot map its peers' buffers (no peer access / IPC in this container), every
@@ -90,6 +90,7 @@ def make_sharded_context(nbx, n: int, exchange: int | None = None, device: int |
     ctx.exchange_used = exchange if world > 1 else None
     if world > 1:
         ctx.set_option("exchange", exchange)
+        ctx.set_option("multicast", multicast)
         uid = nbx.comm_unique_id() if rank == 0 else None
         uid = broadcast_bytes(uid, nbx.UNIQUE_ID_BYTES, src=0)
         ctx.comm_init(uid)
@@ -112,4 +113,5 @@ def make_sharded_context(nbx, n: int, exchange: int | None = None, device: int |
                           f"all ranks use the NCCL all-gather", file=sys.stderr)
                 ctx.set_option("exchange", nbx.EXCHANGE_NCCL)
                 ctx.exchange_used = nbx.EXCHANGE_NCCL
+    ctx.multicast = bool(world > 1 and ctx.info()["multicast"])      # P2P stores go through an NVSwitch multicast team
     return ctx
