@@ -175,8 +175,10 @@ def test_default_plan_multi_gpu_vs_reference_fixture(nbx, world, name):
         ke, secs = nbx.run_group(ctxs, steps)
         info = ctxs[0].info()
         assert info["exchange"] == nbx.EXCHANGE_P2P
-        if name != "n262144":
+        if (world, name) in ((2, "c2"), (8, "c3")):        # 512 tiles per GPU: 444 run unsplit, 68 are split
             assert 0 < info["whole_tiles"] < info["i_tiles"] and info["j_splits"] > 1
+        else:
+            assert info["j_splits"] > 1
         out = [np.zeros(n, dtype=np.float32) for _ in range(6)]
         for c in ctxs:
             c.download_shard(*out)          # every rank contributes its own slice of all six arrays
