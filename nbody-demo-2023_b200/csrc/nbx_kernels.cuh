@@ -16,9 +16,14 @@
 //   * each thread register-blocks R = 2*R2 i-bodies and evaluates every (i, j-pair)
 //     with 12 packed FP32 instructions + 2 MUFU.RSQ, i.e. 12 FP32-pipe lane-ops and
 //     7 issue slots per pair instead of 13 -- the FP32 pipe, not issue, is the limit;
+//   * float sums are kept short: the lane accumulators are folded into a second float per
+//     (body, component) in shared memory every 64 j tiles (two-level accumulation, the default;
+//     a single accumulator over 5e5 terms is biased low by 2e-5 .. 7e-5 at N = 1 M);
 //   * the Euler update, the kinetic-energy reduction (deterministic: per-CTA partial,
 //     last CTA sums in tile order) and, on several GPUs, the NVLink stores of the
-//     updated records into every peer's replica all run in the same kernel's epilogue;
+//     updated records into every peer's replica -- one NVSwitch multicast store per half
+//     record where a multicast team exists -- all run in the same kernel's epilogue; the
+//     wait for the peers' previous step at the top of the kernel is bounded by %globaltimer;
 //   * a j-split with a last-arriver combine in fixed split order fills the 148 SMs: the first
 //     `whole_tiles` i-tiles (whole rounds of the SM count, when there are at least three) run
 //     unsplit, the remaining tail tiles are cut `j_splits` ways along j.  (A persistent stream-K
