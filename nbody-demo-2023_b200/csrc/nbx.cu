@@ -123,7 +123,9 @@ static const std::vector<Variant> &variants()
         // "_f2" = two-level float accumulation (lane sums folded into a second float in shared memory every
         // 64 j tiles): removes the systematic low bias of long float sums for 0.4% of throughput
         // (profiles/r02d_*: N = 1 M kinetic energy 2e-7 from the fp64 truth instead of 1.8e-4)
-        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024>("r4_t256_u4_stage_f2"),   // [0] default for large shards (kLargeVariant)
+        // (248 << 12): the four bodies are walked in reverse order in every stage of the loop body -- the fastest of 52
+        // semantically equivalent source orders on the final source (ptxas register assignment; profiles/r02_ab_perm_*)
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (248 << 12)>("r4_t256_u4_stage_f2"),   // [0] default for large shards (kLargeVariant)
         make_variant<1, 128, 256, 4, 4, 6>("r2_t128_u4"),                            // [1] default for small shards (kSmallVariant)
         make_variant<2, 256, 256, 4, 4, 2, 48>("r4_t256_u4_stage_acc64"),            // [2] accuracy option (kAccurateVariant)
         make_variant<2, 256, 256, 4, 4, 2, 16>("r4_t256_u4_stage"),                  // [3] one float accumulator per lane, like the reference's loops
@@ -141,6 +143,15 @@ static const std::vector<Variant> &variants()
         make_variant<2, 256, 256, 4, 4, 2, 16 | 256>("r4_t256_u4_stage_f2p4"),           // fold every 4 tiles: -3%
         make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 512>("r4_t256_u4_stage_f2p16"),    // every 16: -0.5%
         make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1536>("r4_t256_u4_stage_f2p256"),
+        // source-order permutations (MATH bits 12-19; see PERM in nbx_kernels.cuh): same arithmetic, 2569 .. 2699 G pairs/s at N = 1 M
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024>("r4_t256_u4_stage_f2_perm0"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (1 << 12)>("r4_t256_u4_stage_f2_perm1"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (3 << 12)>("r4_t256_u4_stage_f2_perm3"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (8 << 12)>("r4_t256_u4_stage_f2_perm8"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (16 << 12)>("r4_t256_u4_stage_f2_perm16"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (184 << 12)>("r4_t256_u4_stage_f2_perm184"),
+        make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | (8 << 12)>("r4_t256_u2_stage_f2_perm8"),
+        make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | (248 << 12)>("r4_t256_u2_stage_f2_perm248"),
         make_variant<2, 256, 256, 4, 4, 2>("r4_t256_u4"),
         make_variant<2, 256, 256, 4, 1, 2>("r4_t256_u1"),
         make_variant<3, 256, 256, 4, 2, 2>("r6_t256_u2"),

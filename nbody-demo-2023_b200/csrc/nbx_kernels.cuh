@@ -389,20 +389,44 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                     // stage-major source order (all subtracts, then all r^2, ...): same arithmetic
                     float2 dx[R], dy[R], dz[R], sv[R];
 #pragma unroll
-                    for (int b = 0; b < R; ++b) { dx[b] = __fadd2_rn(xj, nx[b]); dy[b] = __fadd2_rn(yj, ny[b]); dz[b] = __fadd2_rn(zj, nz[b]); }
+                    for (int bb = 0; bb < R; ++bb) {
+                        const int b = ((MATH >> 12) & 16) ? R - 1 - bb : bb;
+                        dx[b] = __fadd2_rn(xj, nx[b]); dy[b] = __fadd2_rn(yj, ny[b]); dz[b] = __fadd2_rn(zj, nz[b]);
+                    }
 #pragma unroll
-                    for (int b = 0; b < R; ++b) sv[b] = __ffma2_rn(dx[b], dx[b], eps2v);
+                    // PERM (MATH bits 12-15, ablation only): semantically equivalent source orders.  ptxas's register
+                    // assignment -- and with it the operand-bank behaviour of the three-operand FFMA2s -- depends on
+                    // the source order at the 1-3 % level; tools/ab.py picks the fastest on the final source.
+                    constexpr int PERM = (MATH >> 12) & 255;
+                    auto rv = [](int bit, int b) { return (PERM & bit) ? R - 1 - b : b; };   // stage-wise reversed body order
+                    if (PERM & 2) {
 #pragma unroll
-                    for (int b = 0; b < R; ++b) sv[b] = __ffma2_rn(dy[b], dy[b], sv[b]);
+                        for (int b = 0; b < R; ++b) sv[b] = __ffma2_rn(dz[b], dz[b], eps2v);
 #pragma unroll
-                    for (int b = 0; b < R; ++b) sv[b] = __ffma2_rn(dz[b], dz[b], sv[b]);
+                        for (int b = 0; b < R; ++b) sv[b] = __ffma2_rn(dy[b], dy[b], sv[b]);
 #pragma unroll
-                    for (int b = 0; b < R; ++b) sv[b] = make_float2(rsqrt_approx(sv[b].x), rsqrt_approx(sv[b].y));
+                        for (int b = 0; b < R; ++b) sv[b] = __ffma2_rn(dx[b], dx[b], sv[b]);
+                    } else {
 #pragma unroll
-                    for (int b = 0; b < R; ++b) {
-                        const float2 inv2 = __fmul2_rn(sv[b], sv[b]);
-                        const float2 mi = __fmul2_rn(mj, sv[b]);
-                        sv[b] = __fmul2_rn(inv2, mi);
+                        for (int b = 0; b < R; ++b) sv[rv(32, b)] = __ffma2_rn(dx[rv(32, b)], dx[rv(32, b)], eps2v);
+#pragma unroll
+                        for (int b = 0; b < R; ++b) sv[rv(32, b)] = __ffma2_rn(dy[rv(32, b)], dy[rv(32, b)], sv[rv(32, b)]);
+#pragma unroll
+                        for (int b = 0; b < R; ++b) sv[rv(32, b)] = __ffma2_rn(dz[rv(32, b)], dz[rv(32, b)], sv[rv(32, b)]);
+                    }
+#pragma unroll
+                    for (int b = 0; b < R; ++b) sv[rv(64, b)] = make_float2(rsqrt_approx(sv[rv(64, b)].x), rsqrt_approx(sv[rv(64, b)].y));
+#pragma unroll
+                    for (int bb = 0; bb < R; ++bb) {
+                        const int b = rv(128, bb);
+                        if (PERM & 1) {
+                            const float2 t = __fmul2_rn(mj, sv[b]);
+                            sv[b] = __fmul2_rn(__fmul2_rn(t, sv[b]), sv[b]);
+                        } else {
+                            const float2 inv2 = __fmul2_rn(sv[b], sv[b]);
+                            const float2 mi = __fmul2_rn(mj, sv[b]);
+                            sv[b] = __fmul2_rn(inv2, mi);
+                        }
                     }
                     if (MATH & 128) {
                         // ablation: accumulate sum s*r_j and sum s (the j operand is shared by the R bodies, so the
@@ -416,9 +440,17 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                         for (int b = 0; b < R; ++b) az[b] = __ffma2_rn(zj, sv[b], az[b]);
 #pragma unroll
                         for (int b = 0; b < R; ++b) as[b] = __fadd2_rn(as[b], sv[b]);
+                    } else if (PERM & 4) {
+#pragma unroll
+                        for (int b = 0; b < R; ++b) ax[(PERM & 8) ? R - 1 - b : b] = __ffma2_rn(dx[(PERM & 8) ? R - 1 - b : b], sv[(PERM & 8) ? R - 1 - b : b], ax[(PERM & 8) ? R - 1 - b : b]);
+#pragma unroll
+                        for (int b = 0; b < R; ++b) ay[(PERM & 8) ? R - 1 - b : b] = __ffma2_rn(dy[(PERM & 8) ? R - 1 - b : b], sv[(PERM & 8) ? R - 1 - b : b], ay[(PERM & 8) ? R - 1 - b : b]);
+#pragma unroll
+                        for (int b = 0; b < R; ++b) az[(PERM & 8) ? R - 1 - b : b] = __ffma2_rn(dz[(PERM & 8) ? R - 1 - b : b], sv[(PERM & 8) ? R - 1 - b : b], az[(PERM & 8) ? R - 1 - b : b]);
                     } else {
 #pragma unroll
-                        for (int b = 0; b < R; ++b) {
+                        for (int bb = 0; bb < R; ++bb) {
+                            const int b = (PERM & 8) ? R - 1 - bb : bb;
                             ax[b] = __ffma2_rn(dx[b], sv[b], ax[b]);
                             ay[b] = __ffma2_rn(dy[b], sv[b], ay[b]);
                             az[b] = __ffma2_rn(dz[b], sv[b], az[b]);

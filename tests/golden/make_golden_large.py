@@ -34,6 +34,7 @@ CASES = {
     "c3": dict(n=1 << 22, steps=1, ic="plummer"),
     "c1": dict(n=16384, steps=500, ic="uniform"),
     "c1s10": dict(n=16384, steps=10, ic="uniform"),        # the same run after 10 steps (the north star's position gate)
+    "c2s10": dict(n=1 << 20, steps=10, ic="uniform"),      # C2 after 10 steps (~15 min reference, ~65 min fp64 truth on 8 cores)
 }
 NSEL = 4096
 
