@@ -1005,6 +1005,7 @@ int nbx_run(nbx_ctx *c, int nsteps, double *kenergy_out, double *seconds_out)
         // In-stream barrier: no rank starts stepping before every rank has enqueued this run (and so has
         // finished its nbx_upload: a peer's epilogue stores into OUR replica) -- and the in-kernel
         // peer wait then only ever covers the skew between GPUs that ARE stepping.
+        CU(cudaMemsetAsync(c->counters + 4, 0, sizeof(int), c->stream));
         NC(g_nccl.AllReduce(c->counters + 4, c->counters + 4, 1, ncclInt, ncclSum, c->comm, c->stream));
     }
     CU(cudaMemsetAsync(c->counters + 1, 0, sizeof(int), c->stream));   // dev_step = 0

@@ -2,7 +2,7 @@
 """The reference's own CPU versions on this box's host cores (SURVEY.md 8d "CPU baseline timing"):
 ver0 single-thread at C0, ver7 and ver8 on all cores at several N.  Uses oracle/_ref (the unmodified
 reference compiled by oracle/Makefile).  Writes gpurun_out/cpu_baselines.json.
-    python tools/cpu_baselines.py [budget_seconds_per_case]"""
+    python tests/cpu_baselines.py [budget_seconds_per_case]"""
 import json, os, platform, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import oracle as O

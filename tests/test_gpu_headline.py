@@ -101,6 +101,14 @@ def test_c2_1m_2_steps(nbx):
     assert g_t[0] < 1e-5 and g_t[1] < 1e-5          # two-level accumulation: far inside the gate
 
 
+def test_c2_1m_10_steps(nbx):
+    """The north star's statement at the headline size itself: N = 1,048,576, kinetic energy per step and
+    positions after 10 steps (fixtures: ver8 and the all-double run, ~15 and ~65 min of 8 CPU cores)."""
+    ref, ke, out, info, _ = run_case(nbx, "c2s10")
+    assert int(ref["steps"]) == 10
+    check_against_fixtures(ref, load("c2s10", "truth", "fp64"), ke, out, "C2 N=1M")
+
+
 def test_c3_4m_plummer_1_step(nbx):
     """BASELINE config 3 (N = 4,194,304 Plummer sphere) on one GPU, one step."""
     ref, ke, out, info, secs = run_case(nbx, "c3")

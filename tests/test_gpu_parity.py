@@ -454,3 +454,15 @@ def test_accurate_option(nbx, oracle):
     err = np.linalg.norm(acc[sel] - truth, axis=1) / np.linalg.norm(truth, axis=1)
     print(f"\naccurate option, N = 1 M sampled forces vs fp64: median {np.median(err):.2e} max {np.max(err):.2e}")
     assert np.max(err) < 1e-5
+
+
+def test_trace_is_a_separate_build(nbx):
+    """Per-CTA timestamps exist only in libnbx_trace.so; the product library says so instead of returning zeros."""
+    with nbx.Context(4096) as c:
+        c.upload(*nbx.ic(4096))
+        c.run(2)
+        with pytest.raises(nbx.NbxError) as e:
+            c.trace()
+        assert e.value.code == nbx.ERR_STATE and "NBX_TRACE" in str(e.value)
+        with pytest.raises(nbx.NbxError):
+            c.set_option("trace_steps", 4)

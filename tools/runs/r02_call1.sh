@@ -21,23 +21,7 @@ NBX_LIB=libnbx_ablation.so python tools/ab.py 262144 4 5 r4_t256_u4_stage,r4_t25
 echo "== A/B inner loop 1M"
 NBX_LIB=libnbx_ablation.so python tools/ab.py 1048576 1 3 r4_t256_u4_stage,r4_t256_u2_stage_occ3,r4_t256_u4_stage_xjacc,r4_t256_u4_stage_s8 0 0 > $O/r02_ab_1m.log 2>&1; cat $O/r02_ab_1m.log
 echo "== accuracy of the xj-accumulate shape"
-NBX_LIB=libnbx_ablation.so python - > $O/r02_xjacc_accuracy.log 2>&1 <<'PY'
-import importlib, sys, numpy as np
-sys.path.insert(0, ".")
-nbx = importlib.import_module("nbody-demo-2023_b200").nbx
-from oracle import oracle as O
-names = nbx.variant_names()
-for n in (65536, 1 << 20):
-    arrs = nbx.ic(n); s = O.State(n)
-    for f, a in zip(O.State.FIELDS, arrs): setattr(s, f, a)
-    sel = np.random.default_rng(5).choice(n, 256, replace=False).astype(np.int32)
-    truth = O.acc_fp64(s, sel); tn = np.linalg.norm(truth, axis=1)
-    for nm in ("r4_t256_u4_stage", "r4_t256_u4_stage_xjacc"):
-        with nbx.Context(n) as c:
-            c.set_option("variant", names.index(nm)); c.upload(*arrs); acc = c.accelerations()[sel]
-        e = np.linalg.norm(acc - truth, axis=1) / tn
-        print(f"N={n} {nm:28s} sampled force error vs fp64: median {np.median(e):.2e} max {e.max():.2e}")
-PY
+python tests/accuracy_probe.py forces 65536 r4_t256_u4_stage,r4_t256_u4_stage_xjacc > $O/r02_xjacc_accuracy.log 2>&1; python tests/accuracy_probe.py forces 1048576 r4_t256_u4_stage,r4_t256_u4_stage_xjacc >> $O/r02_xjacc_accuracy.log 2>&1
 cat $O/r02_xjacc_accuracy.log
 echo "== ncu C1 (after a plain run of the same command)"
 python tools/run_steps.py 16384 30 graph=0 > $O/r02_ncu_c1_plain.log 2>&1 && \
