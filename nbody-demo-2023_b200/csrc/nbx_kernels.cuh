@@ -393,10 +393,10 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                         const int b = ((MATH >> 12) & 16) ? R - 1 - bb : bb;
                         dx[b] = __fadd2_rn(xj, nx[b]); dy[b] = __fadd2_rn(yj, ny[b]); dz[b] = __fadd2_rn(zj, nz[b]);
                     }
-#pragma unroll
-                    // PERM (MATH bits 12-15, ablation only): semantically equivalent source orders.  ptxas's register
-                    // assignment -- and with it the operand-bank behaviour of the three-operand FFMA2s -- depends on
-                    // the source order at the 1-3 % level; tools/ab.py picks the fastest on the final source.
+                    // PERM (MATH bits 12-19): semantically equivalent source orders.  ptxas's register assignment -- and
+                    // with it the operand-bank behaviour of the three-operand FFMA2s -- depends on the source order at
+                    // the 1-5 % level; the default (248: bodies walked in reverse in every stage) is the fastest of 52
+                    // orders A/B-ed on the final source (profiles/r02_ab_perm_*.log).
                     constexpr int PERM = (MATH >> 12) & 255;
                     auto rv = [](int bit, int b) { return (PERM & bit) ? R - 1 - b : b; };   // stage-wise reversed body order
                     if (PERM & 2) {
