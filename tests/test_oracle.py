@@ -172,3 +172,46 @@ def test_large_fixtures_are_consistent_with_the_small_ones(golden):
         f = np.load(os.path.join(GOLDEN_DIR, f"large_{name}_ver8.npz"))
         assert int(f["n"]) == n and f["ke"].size == steps and f["pos_sel"].shape == (4096, 3)
         assert np.all(np.diff(f["sel"]) > 0) and np.all(np.isfinite(f["ke"]))
+
+
+def _dev(fx, tr):
+    ke = float(np.max(np.abs(fx["ke"].astype(np.float64) - tr["ke"]) / tr["ke"]))
+    return ke, rel_l2(fx["pos_sel"], tr["pos_sel"]), rel_l2(fx["vel_sel"], tr["vel_sel"])
+
+
+def test_reference_output_vs_fp64_truth_is_as_documented():
+    """The claim the large-N parity gates rest on, checkable without a GPU: the reference's own
+    float output (ver8 fixtures) is within 1e-4 of the all-double run up to N = 262 144 and NOT beyond."""
+    import os
+    from conftest import GOLDEN_DIR
+
+    def pair(name):
+        return (np.load(os.path.join(GOLDEN_DIR, f"large_{name}_ver8.npz")), np.load(os.path.join(GOLDEN_DIR, f"truth_{name}_fp64.npz")))
+    ke, pos, vel = _dev(*pair("c1s10"))
+    assert ke < 2e-6 and pos < 1e-6 and vel < 2e-6
+    ke, pos, vel = _dev(*pair("n262144"))
+    assert 2e-5 < ke < 1e-4 and pos < 1e-4 and vel < 1e-4
+    ke, pos, vel = _dev(*pair("c2"))
+    assert 5e-4 < ke < 1.2e-3 and 3e-4 < pos < 8e-4 and 3e-4 < vel < 8e-4          # 8.3e-4 / 5.3e-4 / 5.1e-4
+    ke, pos, vel = _dev(*pair("c3"))
+    assert 1.5e-3 < ke < 4e-3 and 6e-4 < pos < 2e-3 and 8e-4 < vel < 2e-3          # 2.5e-3 / 1.1e-3 / 1.3e-3
+    ke, pos, vel = _dev(*pair("c1"))                                               # 500 steps: chaotic
+    assert 2e-4 < ke < 1e-3 and vel > 5e-3
+    for name in ("c1s10", "n262144", "c2", "c3", "c1"):
+        fx, tr = pair(name)
+        assert np.array_equal(fx["sel"], tr["sel"]) and int(fx["n"]) == int(tr["n"]) and int(fx["steps"]) == int(tr["steps"])
+
+
+def test_truth_fixture_is_reproducible(oracle):
+    """tests/golden/truth_c1s10_fp64.npz regenerated here with oracle_run_fp64 (2 s): same numbers."""
+    import os
+    from conftest import GOLDEN_DIR
+    tr = np.load(os.path.join(GOLDEN_DIR, "truth_c1s10_fp64.npz"))
+    s0 = oracle.ic_uniform(int(tr["n"]))
+    pos, vel, ke = oracle.run_fp64(s0, int(tr["steps"]))
+    assert np.max(np.abs(ke - tr["ke"]) / tr["ke"]) < 1e-12
+    assert rel_l2(pos[tr["sel"]], tr["pos_sel"]) < 1e-12 and rel_l2(vel[tr["sel"]], tr["vel_sel"]) < 1e-12
+    # and the float oracle (the reference's ver2 arithmetic) sits where the reference's fixture sits
+    s = s0.copy()
+    ke32 = oracle.run(s, int(tr["steps"]), variant="ver2")
+    assert np.max(np.abs(ke32 - tr["ke"]) / tr["ke"]) < 5e-6
