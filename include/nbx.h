@@ -110,8 +110,11 @@ NBX_API void nbx_destroy(nbx_ctx *ctx);
 /* Tuning / mode knobs; all optional, call before the first nbx_run.
  *   "j_splits"  >=1 force a j-split count, 0 = auto (fills the SMs at small N)
  *   "graph"     1/0 replay steps from a CUDA graph (auto: on for small N)
- *   "accurate"  1/0 two-level accumulation (float per j tile, then double): large-N accuracy option
- *   "pdl"       1/0 programmatic dependent launch between consecutive steps (-1 = auto: many-wave grids only)
+ *   "accurate"  1/0 fold the float lane sums into DOUBLE accumulators every 4 j tiles (forces 3e-8 from fp64 at
+ *               N = 1 M, -3 % throughput).  The default kernel already keeps float sums short (two-level FLOAT
+ *               accumulation, 3e-7); variant 3 is the single-accumulator scheme of the reference's loops.
+ *   "pdl"       1/0 programmatic dependent launch between consecutive steps (-1 = auto: many-wave grids, and
+ *               grids that fit the SMs once -- those are then run one CTA per SM)
  *   "multicast" P2P exchange: -1 auto = use NVSwitch multicast (cuMulticast* + multimem.st) when the driver
  *               offers it, 0 never, 1 fail if unavailable; NBX_VERBOSE=1 prints why it was not used.  Works inside
  *               one process (nbx_run_group / nbx_p2p_attach_group) and across processes (nbx_p2p_attach, when a
