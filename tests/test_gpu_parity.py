@@ -268,9 +268,12 @@ def test_full_size_c2_properties(nbx, oracle):
     d_ref = np.linalg.norm(acc[sel] - ref32, axis=1) / tn
     print(f"\nC2 sampled forces vs fp64: GPU median {np.median(err):.2e} max {np.max(err):.2e}; "
           f"reference float median {np.median(err_ref):.2e} max {np.max(err_ref):.2e}; GPU vs reference float max {np.max(d_ref):.2e}")
-    assert np.median(err) < max(2e-5, 1.5 * np.median(err_ref))
-    assert np.max(err) < max(1e-4, 1.5 * np.max(err_ref))
-    assert np.max(d_ref) < max(1e-4, 2.0 * np.max(err_ref))
+    # fixed gates (round 1 had to scale them with the reference's own float error; the two-level accumulation made
+    # that unnecessary): every sampled force within 1e-5 of the fp64 force, median within 2e-6.  The reference's
+    # float arithmetic itself is printed for scale (2e-4 at this size) and is NOT part of the gate.
+    assert np.median(err) < 2e-6
+    assert np.max(err) < 1e-5
+    assert np.max(d_ref) < 1e-5 + np.max(err_ref)
     dt = np.float32(0.1)
     for k in range(3):
         v_new = arrs[3 + k] + acc[:, k] * dt
@@ -376,9 +379,9 @@ def test_full_size_c3_plummer_properties(nbx, oracle):
     d_ref = np.linalg.norm(acc[sel] - ref32, axis=1) / tn
     print(f"\nC3 sampled forces vs fp64: GPU median {np.median(err):.2e} max {np.max(err):.2e}; "
           f"reference float median {np.median(err_ref):.2e} max {np.max(err_ref):.2e}; GPU vs reference float max {np.max(d_ref):.2e}")
-    assert np.median(err) < max(2e-5, 1.5 * np.median(err_ref))
-    assert np.max(err) < max(1e-4, 1.5 * np.max(err_ref))
-    assert np.max(d_ref) < max(1e-4, 2.0 * np.max(err_ref))
+    assert np.median(err) < 2e-6            # fixed gates, see test_full_size_c2_properties
+    assert np.max(err) < 1e-5
+    assert np.max(d_ref) < 1e-5 + np.max(err_ref)
     dt = np.float32(0.1)
     for k in range(3):
         assert np.allclose(out[3 + k], arrs[3 + k] + acc[:, k] * dt, rtol=1e-6, atol=1e-9)
