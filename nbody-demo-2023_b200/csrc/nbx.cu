@@ -123,9 +123,10 @@ static const std::vector<Variant> &variants()
         // "_f2" = two-level float accumulation (lane sums folded into a second float in shared memory every
         // 64 j tiles): removes the systematic low bias of long float sums for 0.4% of throughput
         // (profiles/r02d_*: N = 1 M kinetic energy 2e-7 from the fp64 truth instead of 1.8e-4)
-        // (248 << 12): the four bodies are walked in reverse order in every stage of the loop body -- the fastest of 52
-        // semantically equivalent source orders on the final source (ptxas register assignment; profiles/r02_ab_perm_*)
-        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (248 << 12)>("r4_t256_u4_stage_f2"),   // [0] default for large shards (kLargeVariant)
+        // (504 << 12): the four bodies are walked in reverse order in every stage of the loop body and the accumulate
+        // takes its multiplicands as (s, d) -- the fastest of 58 semantically equivalent source orders on the final
+        // source (ptxas register assignment / operand slots; profiles/r02_ab_perm_*)
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (504 << 12)>("r4_t256_u4_stage_f2"),   // [0] default for large shards (kLargeVariant)
         make_variant<1, 128, 256, 4, 4, 6>("r2_t128_u4"),                            // [1] default for small shards (kSmallVariant)
         make_variant<2, 256, 256, 4, 4, 2, 48>("r4_t256_u4_stage_acc64"),            // [2] accuracy option (kAccurateVariant)
         make_variant<2, 256, 256, 4, 4, 2, 16>("r4_t256_u4_stage"),                  // [3] one float accumulator per lane, like the reference's loops
@@ -152,6 +153,12 @@ static const std::vector<Variant> &variants()
         make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (184 << 12)>("r4_t256_u4_stage_f2_perm184"),
         make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | (8 << 12)>("r4_t256_u2_stage_f2_perm8"),
         make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | (248 << 12)>("r4_t256_u2_stage_f2_perm248"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (248 << 12)>("r4_t256_u4_stage_f2_perm248"),    // 504 without the swapped accumulate multiplicands
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (760 << 12)>("r4_t256_u4_stage_f2_perm760"),    // 248 + swapped multiplies
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (1016 << 12)>("r4_t256_u4_stage_f2_perm1016"),  // both
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (256 << 12)>("r4_t256_u4_stage_f2_perm256"),
+        make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | (504 << 12)>("r4_t256_u2_stage_f2_perm504"),
+        make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | (264 << 12)>("r4_t256_u2_stage_f2_perm264"),
         make_variant<2, 256, 256, 4, 4, 2>("r4_t256_u4"),
         make_variant<2, 256, 256, 4, 1, 2>("r4_t256_u1"),
         make_variant<3, 256, 256, 4, 2, 2>("r6_t256_u2"),

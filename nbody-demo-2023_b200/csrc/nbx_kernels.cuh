@@ -393,11 +393,11 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                         const int b = ((MATH >> 12) & 16) ? R - 1 - bb : bb;
                         dx[b] = __fadd2_rn(xj, nx[b]); dy[b] = __fadd2_rn(yj, ny[b]); dz[b] = __fadd2_rn(zj, nz[b]);
                     }
-                    // PERM (MATH bits 12-19): semantically equivalent source orders.  ptxas's register assignment -- and
+                    // PERM (MATH bits 12-21): semantically equivalent source orders.  ptxas's register assignment -- and
                     // with it the operand-bank behaviour of the three-operand FFMA2s -- depends on the source order at
-                    // the 1-5 % level; the default (248: bodies walked in reverse in every stage) is the fastest of 52
-                    // orders A/B-ed on the final source (profiles/r02_ab_perm_*.log).
-                    constexpr int PERM = (MATH >> 12) & 255;
+                    // the 1-5 % level; the default (504: bodies walked in reverse in every stage, accumulate written
+                    // as s*d + acc) is the fastest of 58 orders A/B-ed on the final source (profiles/r02_ab_perm_*.log).
+                    constexpr int PERM = (MATH >> 12) & 1023;
                     auto rv = [](int bit, int b) { return (PERM & bit) ? R - 1 - b : b; };   // stage-wise reversed body order
                     if (PERM & 2) {
 #pragma unroll
@@ -424,8 +424,8 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                             sv[b] = __fmul2_rn(__fmul2_rn(t, sv[b]), sv[b]);
                         } else {
                             const float2 inv2 = __fmul2_rn(sv[b], sv[b]);
-                            const float2 mi = __fmul2_rn(mj, sv[b]);
-                            sv[b] = __fmul2_rn(inv2, mi);
+                            const float2 mi = (PERM & 512) ? __fmul2_rn(sv[b], mj) : __fmul2_rn(mj, sv[b]);
+                            sv[b] = (PERM & 512) ? __fmul2_rn(mi, inv2) : __fmul2_rn(inv2, mi);
                         }
                     }
                     if (MATH & 128) {
@@ -451,9 +451,15 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
 #pragma unroll
                         for (int bb = 0; bb < R; ++bb) {
                             const int b = (PERM & 8) ? R - 1 - bb : bb;
-                            ax[b] = __ffma2_rn(dx[b], sv[b], ax[b]);
-                            ay[b] = __ffma2_rn(dy[b], sv[b], ay[b]);
-                            az[b] = __ffma2_rn(dz[b], sv[b], az[b]);
+                            if (PERM & 256) {      // multiplicands swapped: the other operand slots of the FFMA2
+                                ax[b] = __ffma2_rn(sv[b], dx[b], ax[b]);
+                                ay[b] = __ffma2_rn(sv[b], dy[b], ay[b]);
+                                az[b] = __ffma2_rn(sv[b], dz[b], az[b]);
+                            } else {
+                                ax[b] = __ffma2_rn(dx[b], sv[b], ax[b]);
+                                ay[b] = __ffma2_rn(dy[b], sv[b], ay[b]);
+                                az[b] = __ffma2_rn(dz[b], sv[b], az[b]);
+                            }
                         }
                     }
                 } else
