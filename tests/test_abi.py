@@ -136,13 +136,15 @@ def test_header_is_plain_c(tmp_path):
     src.write_text('#include "nbx.h"\n#include <stdio.h>\nint main(void){ int n = -1; nbx_ctx *c = 0;'
                    ' if (nbx_abi_version() != NBX_ABI_VERSION) return 2; if (nbx_device_count(&n)) return 3;'
                    ' if (n == 0 && nbx_create(&c, 16, 0, 0, 1, 0.1f, 6.67259e-11f, 1e-3f) != NBX_ERR_NODEVICE) return 4;'
-                   ' if (c) nbx_destroy(c); printf("%d %s\\n", n, nbx_last_error()); return 0; }\n')
+                   ' if (c) nbx_destroy(c); printf("%d %d %s\\n", n, (int)sizeof(nbx_info), nbx_last_error()); return 0; }\n')
     exe = tmp_path / "t"
     r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe),
                         "-L", pkg.PKG_DIR, "-lnbx", "-Wl,-rpath," + pkg.PKG_DIR], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    # the ctypes mirror of nbx_info has the C layout (guards against ABI drift between include/nbx.h and nbx.py)
+    assert int(r.stdout.split()[1]) == ctypes.sizeof(pkg.nbx.Info)
 
 
 def test_launch_plan_host_logic(nbx):
