@@ -193,11 +193,13 @@ def test_reference_output_vs_fp64_truth_is_as_documented():
     assert 2e-5 < ke < 1e-4 and pos < 1e-4 and vel < 1e-4
     ke, pos, vel = _dev(*pair("c2"))
     assert 5e-4 < ke < 1.2e-3 and 3e-4 < pos < 8e-4 and 3e-4 < vel < 8e-4          # 8.3e-4 / 5.3e-4 / 5.1e-4
+    ke, pos, vel = _dev(*pair("c2s10"))                                            # ... and stays there over 10 steps
+    assert 5e-4 < ke < 1.2e-3 and 3e-4 < pos < 8e-4 and 3e-4 < vel < 8e-4          # 8.6e-4 / 5.3e-4 / 5.3e-4
     ke, pos, vel = _dev(*pair("c3"))
     assert 1.5e-3 < ke < 4e-3 and 6e-4 < pos < 2e-3 and 8e-4 < vel < 2e-3          # 2.5e-3 / 1.1e-3 / 1.3e-3
     ke, pos, vel = _dev(*pair("c1"))                                               # 500 steps: chaotic
     assert 2e-4 < ke < 1e-3 and vel > 5e-3
-    for name in ("c1s10", "n262144", "c2", "c3", "c1"):
+    for name in ("c1s10", "n262144", "c2", "c2s10", "c3", "c1"):
         fx, tr = pair(name)
         assert np.array_equal(fx["sel"], tr["sel"]) and int(fx["n"]) == int(tr["n"]) and int(fx["steps"]) == int(tr["steps"])
 
