@@ -520,8 +520,8 @@ def main():
             finally:
                 c2.close()
 
-        # NVSwitch multicast needs ONE process driving all the GPUs (the multicast handle is not exported across
-        # processes): rank 0 runs the same workload through nbx_run_group while the other ranks wait on a CPU barrier
+        # the one-process form of the same run (nbx_run_group: the CLI's path; its multicast team needs no descriptor
+        # passing): rank 0 drives all the GPUs while the other ranks wait on a CPU barrier
         gloo = torch.distributed.new_group(backend="gloo")
         if rank == 0:
             try:
