@@ -6,8 +6,8 @@
 // main.cpp GSimulation.cpp).  This file is that one translation unit for ARCH=b200.  It is
 // compiled against the reference's UNMODIFIED GSimulation.hpp / GSimulation.cpp / main.cpp:
 //
-//   g++ -std=c++14 -O2 -I$REF/ver5_all -I$NBX/include \
-//       $NBX/integration/b200/Compute.cpp $REF/ver5_all/main.cpp $REF/ver5_all/GSimulation.cpp \
+//   g++ -std=c++14 -O2 -I$REF/ver5_all -I$NBX/include
+//       $NBX/integration/b200/Compute.cpp $REF/ver5_all/main.cpp $REF/ver5_all/GSimulation.cpp
 //       -L$NBX/nbody-demo-2023_b200 -lnbx -Wl,-rpath,$NBX/nbody-demo-2023_b200 -o nbody.x
 //
 // (tests/test_integration_link.py does exactly this and checks the table the binary prints.)
