@@ -159,6 +159,11 @@ static const std::vector<Variant> &variants()
         make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (256 << 12)>("r4_t256_u4_stage_f2_perm256"),
         make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | (504 << 12)>("r4_t256_u2_stage_f2_perm504"),
         make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | (264 << 12)>("r4_t256_u2_stage_f2_perm264"),
+        // more, smaller CTAs per SM (independent instruction streams): 4 x 128 threads, 8 x 64 threads
+        make_variant<2, 128, 256, 4, 4, 4, 16 | 256 | 1024 | (504 << 12)>("r4_t128_u4_stage_f2"),
+        make_variant<2, 128, 256, 4, 4, 4, 16 | 256 | 1024 | (248 << 12)>("r4_t128_u4_stage_f2_perm248"),
+        make_variant<2, 128, 256, 4, 4, 4, 16 | 256 | 1024>("r4_t128_u4_stage_f2_perm0"),
+        make_variant<2, 64, 256, 4, 4, 8, 16 | 256 | 1024 | (504 << 12)>("r4_t64_u4_stage_f2"),
         make_variant<2, 256, 256, 4, 4, 2>("r4_t256_u4"),
         make_variant<2, 256, 256, 4, 1, 2>("r4_t256_u1"),
         make_variant<3, 256, 256, 4, 2, 2>("r6_t256_u2"),
