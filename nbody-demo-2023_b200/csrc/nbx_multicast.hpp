@@ -268,7 +268,7 @@ inline bool send_fds(int sock, const int *fds, int count)
     cmsghdr *cm = CMSG_FIRSTHDR(&msg);
     cm->cmsg_level = SOL_SOCKET; cm->cmsg_type = SCM_RIGHTS; cm->cmsg_len = CMSG_LEN(sizeof(int) * count);
     std::memcpy(CMSG_DATA(cm), fds, sizeof(int) * count);
-    return sendmsg(sock, &msg, 0) == 1;
+    return sendmsg(sock, &msg, MSG_NOSIGNAL) == 1;      // a peer that went away is an error return, not a SIGPIPE
 }
 
 inline bool recv_fds(int sock, int *fds, int count, int timeout_ms)
@@ -316,11 +316,14 @@ inline std::string mp_open_team(int rank, int world, int device, size_t bytes, c
         mp.numDevices = (unsigned)world;
         mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
         mp.size = size;
+        auto close_fds = [&]() { for (int b = 0; b < nbuf; ++b) if (fds[b] >= 0) { close(fds[b]); fds[b] = -1; } };
         for (int b = 0; b < nbuf; ++b) {
-            if ((r = a.MulticastCreate(&bufs[b].mc, &mp)) != CUDA_SUCCESS) return err("cuMulticastCreate(exportable)", r);
+            if ((r = a.MulticastCreate(&bufs[b].mc, &mp)) != CUDA_SUCCESS) { close_fds(); return err("cuMulticastCreate(exportable)", r); }
             bufs[b].team_refs = new int(1);
-            if ((r = a.MemExportToShareableHandle(&fds[b], bufs[b].mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0)) != CUDA_SUCCESS)
+            if ((r = a.MemExportToShareableHandle(&fds[b], bufs[b].mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0)) != CUDA_SUCCESS) {
+                close_fds();
                 return err("cuMemExportToShareableHandle", r);
+            }
         }
         const int ls = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
         bool good = ls >= 0 && bind(ls, (sockaddr *)&sa, salen) == 0 && listen(ls, world) == 0;
@@ -332,7 +335,7 @@ inline std::string mp_open_team(int rank, int world, int device, size_t bytes, c
             if (cs >= 0) close(cs);
         }
         if (ls >= 0) close(ls);
-        for (int b = 0; b < nbuf; ++b) if (fds[b] >= 0) close(fds[b]);
+        close_fds();
         if (!good) return "could not hand the multicast descriptors to every peer (Unix socket)";
     } else {
         int cs = -1;
@@ -347,12 +350,16 @@ inline std::string mp_open_team(int rank, int world, int device, size_t bytes, c
         const bool got = recv_fds(cs, fds, nbuf, timeout_ms);
         close(cs);
         if (!got) return "did not receive the multicast descriptors";
+        std::string bad;
         for (int b = 0; b < nbuf; ++b) {
-            r = a.MemImportFromShareableHandle(&bufs[b].mc, (void *)(uintptr_t)fds[b], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
-            close(fds[b]);
-            if (r != CUDA_SUCCESS) return err("cuMemImportFromShareableHandle", r);
+            r = bad.empty() ? a.MemImportFromShareableHandle(&bufs[b].mc, (void *)(uintptr_t)fds[b], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR)
+                            : CUDA_SUCCESS;
+            close(fds[b]);                                   // every received descriptor is closed, also after a failure
+            if (!bad.empty()) continue;
+            if (r != CUDA_SUCCESS) { bad = err("cuMemImportFromShareableHandle", r); continue; }
             bufs[b].team_refs = new int(1);
         }
+        if (!bad.empty()) return bad;
     }
     for (int b = 0; b < nbuf; ++b) { bufs[b].size = size; bufs[b].gran = gran; bufs[b].device = device; }
     return "";
