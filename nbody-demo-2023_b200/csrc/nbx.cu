@@ -106,14 +106,13 @@ struct Variant {
     int r2, threads, tj, stages, unroll, minb;
     int smem;
     const void *fn;
-    bool qscale;   // j-records come from the q-scaled array (qscale_kernel runs before every step launch)
 };
 
 template <int R2, int THREADS, int TJ, int STAGES, int UNROLL, int MINB, int MATH = 0>
 static Variant make_variant(const char *name)
 {
     return Variant{name, R2, THREADS, TJ, STAGES, UNROLL, MINB, nbx::step_smem_bytes<THREADS, TJ, STAGES, R2, MATH>(),
-                   (const void *)nbx::step_kernel<R2, THREADS, TJ, STAGES, UNROLL, MINB, MATH>, (MATH & nbx::kMathQScale) != 0};
+                   (const void *)nbx::step_kernel<R2, THREADS, TJ, STAGES, UNROLL, MINB, MATH>};
 }
 
 static const std::vector<Variant> &variants()
@@ -135,16 +134,7 @@ static const std::vector<Variant> &variants()
         make_variant<2, 128, 256, 4, 2, 4>("r4_t128_u2"),
         make_variant<2, 512, 512, 4, 2, 1>("r4_t512_u2"),
         make_variant<2, 64, 128, 4, 2, 8>("r4_t64_u2"),
-        // "_qs": the q-scaled pair, 11 packed FP32 instructions instead of 12 (see the QS block in nbx_kernels.cuh)
-        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (504 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qs"),   // [7]
 #ifdef NBX_ABLATION
-        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | nbx::kMathQScale>("r4_t256_u4_stage_f2_qs_perm0"),
-        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (505 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qs_perm505"),
-        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (248 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qs_perm248"),
-        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (256 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qs_perm256"),
-        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (8 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qs_perm8"),
-        make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | (504 << 12) | nbx::kMathQScale>("r4_t256_u2_stage_f2_qs"),
-        make_variant<2, 256, 256, 4, 4, 2, 16 | (504 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_qs"),
         // Shapes kept only for the tuning tools (tools/sweep.py, tools/ab.py): `make ablation`
         // builds libnbx_ablation.so with them; the product library does not carry them.
         make_variant<2, 256, 256, 4, 2, 2>("r4_t256_u2"),
@@ -192,15 +182,7 @@ static const std::vector<Variant> &variants()
     return v;
 }
 
-constexpr int kLargeVariant = 0, kSmallVariant = 1, kAccurateVariant = 2, kQScaleVariant = 7;
-// From this many bodies on the 11-instruction q-scaled pair is the default (its one extra rounding per body is
-// invisible in a sum over >= 65 536 pairs; below, the 12-instruction pair is kept: tests/qscale_emulation.py).
-constexpr int kQScaleMinBodies = 65536;
-#ifdef NBX_LARGE_QS
-constexpr bool kQScaleDefault = true;
-#else
-constexpr bool kQScaleDefault = false;
-#endif
+constexpr int kLargeVariant = 0, kSmallVariant = 1, kAccurateVariant = 2;
 constexpr int kSmallShardBodies = 8192;   // below this the 256-body CTAs of kSmallVariant fill the SMs better
 
 // ------------------------------------------------------------------------------
@@ -216,7 +198,6 @@ struct nbx_ctx {
     float4 *pos[2] = {nullptr, nullptr};
     int cur = 0;
     float4 *vel = nullptr;
-    float4 *qrec = nullptr;    // q-scaled shapes only: 24 B per body, rewritten before every step launch
     float4 *part = nullptr;
     float4 *acc = nullptr;
     int *tile_ticket = nullptr;
@@ -294,9 +275,7 @@ static Plan make_plan(int n_pad, int i_count, int world, int sm_count, int excha
     Plan p{};
     p.variant = opt_variant >= 0 ? opt_variant
                 : opt_accurate   ? kAccurateVariant
-                : i_count < kSmallShardBodies ? kSmallVariant
-                : (kQScaleDefault && n_pad >= kQScaleMinBodies) ? kQScaleVariant
-                                                                : kLargeVariant;
+                                 : (i_count < kSmallShardBodies ? kSmallVariant : kLargeVariant);
     const Variant &v = variants()[p.variant];
     const int bi = v.threads * v.r2 * 2;
     p.i_tiles = (i_count + bi - 1) / bi;
@@ -371,8 +350,6 @@ static int resolve(nbx_ctx *c)
     c->ctas_per_sm = occ;
 
     if (c->part) { CU(cudaFree(c->part)); c->part = nullptr; }
-    if (c->qrec) { CU(cudaFree(c->qrec)); c->qrec = nullptr; }
-    if (v.qscale) CU(cudaMalloc(&c->qrec, (size_t)c->n_pad * 24));
     if (c->tile_ticket) { CU(cudaFree(c->tile_ticket)); c->tile_ticket = nullptr; }
     if (c->ke_part) { CU(cudaFree(c->ke_part)); c->ke_part = nullptr; }
     if (splits > 1) CU(cudaMalloc(&c->part, (size_t)splits * c->split_bodies * sizeof(float4)));
@@ -399,7 +376,6 @@ static void fill_params(const nbx_ctx *c, StepParams &p, int in_buf, float4 *acc
     std::memset(&p, 0, sizeof p);
     p.pos_in = c->pos[in_buf];
     p.pos_out = c->pos[in_buf ^ 1];
-    p.qrec = c->qrec;
     p.vel = c->vel;
     p.part = c->part;
     p.tile_ticket = c->tile_ticket;
@@ -458,13 +434,6 @@ static int launch_step(nbx_ctx *c, int in_buf, float4 *acc_out = nullptr, int ph
     StepParams p;
     fill_params(c, p, in_buf, acc_out, phase);
     void *args[] = {&p};
-    if (v.qscale) {
-        // the launch's j window, in records; a plain launch: it starts when the previous step has completed
-        const int rec_org = p.j_org >> 1, rec_len = p.j_len >> 1;
-        nbx::qscale_kernel<<<(rec_len + 255) / 256, 256, 0, c->stream>>>(p, rec_org, rec_len);
-        CU(cudaGetLastError());
-        c->aux_launches++;
-    }
     const int ctas = c->whole_tiles + (c->i_tiles - c->whole_tiles) * p.j_splits;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
@@ -487,13 +456,12 @@ static int launch_step(nbx_ctx *c, int in_buf, float4 *acc_out = nullptr, int ph
 static int build_graph(nbx_ctx *c, int steps, cudaGraphExec_t *out)
 {
     cudaGraph_t g = nullptr;
-    const long long before = c->kernel_launches, before_aux = c->aux_launches;
+    const long long before = c->kernel_launches;
     CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     int rc = NBX_OK;
     for (int s = 0; s < steps && rc == NBX_OK; ++s) rc = launch_step(c, s & 1);
     cudaError_t e = cudaStreamEndCapture(c->stream, &g);
     c->kernel_launches = before;   // capturing is not launching
-    c->aux_launches = before_aux;
     if (rc != NBX_OK) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(NBX_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
     e = cudaGraphInstantiate(out, g, 0);
@@ -594,14 +562,12 @@ static int enqueue_steps(nbx_ctx *c, int nsteps)
         while (left >= 16) {
             CU(cudaGraphLaunch(c->graph16, c->stream));
             c->kernel_launches += 16;
-            if (variants()[c->variant].qscale) c->aux_launches += 16;
             left -= 16;
         }
         if (left >= 2 && !c->graph2) { int rc = build_graph(c, 2, &c->graph2); if (rc) return rc; }
         while (left >= 2) {
             CU(cudaGraphLaunch(c->graph2, c->stream));
             c->kernel_launches += 2;
-            if (variants()[c->variant].qscale) c->aux_launches += 2;
             left -= 2;
         }
     }
@@ -732,7 +698,7 @@ void nbx_destroy(nbx_ctx *c)
         cudaFree(c->pos[0]); cudaFree(c->pos[1]);
     }
     cudaFree(c->retired_pos[0]); cudaFree(c->retired_pos[1]);
-    cudaFree(c->vel); cudaFree(c->qrec); cudaFree(c->part); cudaFree(c->acc);
+    cudaFree(c->vel); cudaFree(c->part); cudaFree(c->acc);
     cudaFree(c->tile_ticket); cudaFree(c->ke_part); cudaFree(c->counters); cudaFree(c->flags);
     cudaFree(c->ke_dev); cudaFree(c->stage); cudaFree(c->trace);
     if (c->ev0) cudaEventDestroy(c->ev0);

@@ -75,11 +75,7 @@ struct StepParams {
     // Trace build (-DNBX_TRACE, libnbx_trace.so) only: per-CTA %globaltimer stamps, kTraceWords per CTA per step
     unsigned long long *trace;
     int trace_steps;                  // steps the buffer holds (later steps are not recorded)
-    // q-scaled shapes (MATH bit kMathQScale) only: the j-records in the form the 11-instruction pair needs,
-    // 48 bytes per body pair, rewritten from pos_in by qscale_kernel before every step launch
-    float4 *qrec;
 };
-constexpr int kMathQScale = 1 << 22;
 constexpr int kTraceWords = 6;        // start, first tile landed, sweep done, exit, smid, last-arriver flag
 
 // Values of *dev_err (low byte; the rest carries detail: peer rank << 8, or source line << 8).
@@ -201,13 +197,11 @@ template <bool SCALAR> __device__ __forceinline__ float2 fma2(float2 a, float2 b
 }
 
 // Shared-memory footprint of one CTA (host uses the same formula).  MATH bit 32 ("acc64") adds
-// one double per (i-body, component) per thread: the second accumulation level; q-scaled shapes
-// stream 24 instead of 16 bytes per j-body.
+// one double per (i-body, component) per thread: the second accumulation level.
 template <int THREADS, int TJ, int STAGES, int R2 = 0, int MATH = 0>
 __host__ __device__ constexpr int step_smem_bytes()
 {
-    return STAGES * TJ * ((MATH & kMathQScale) ? 24 : 16) + 2 * STAGES * 8 + (THREADS / 32) * 8 + 16 +
-           ((MATH & 32) ? 3 * 2 * R2 * THREADS * 8 : 0) +
+    return STAGES * TJ * 16 + 2 * STAGES * 8 + (THREADS / 32) * 8 + 16 + ((MATH & 32) ? 3 * 2 * R2 * THREADS * 8 : 0) +
            ((MATH & 256) ? 3 * 2 * R2 * THREADS * 4 : 0);
 }
 
@@ -230,9 +224,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
-    constexpr bool QS = (MATH & kMathQScale) != 0;
-    constexpr int JB = QS ? 24 : 16;                         // bytes per j-body in the ring
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + STAGES * TJ * JB);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + STAGES * TJ * 16);
     uint64_t *empty = full + STAGES;
     double *red = reinterpret_cast<double *>(empty + STAGES);
     int *s_flag = reinterpret_cast<int *>(red + WARPS);
@@ -240,14 +232,14 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     // a double per (body, component) after every 4th j tile, so no float sum is longer than 2*TJ terms:
     // the large-N float summation error (1e-4 at 1 M, 1e-3 at 4 M for the reference's single
     // accumulator) drops to the 1e-6 level for ~1% time.  hi[q * THREADS + tid]: conflict-free.
-    double *hi = reinterpret_cast<double *>(smem_raw + step_smem_bytes<THREADS, TJ, STAGES, 0, MATH & kMathQScale>());
+    double *hi = reinterpret_cast<double *>(smem_raw + step_smem_bytes<THREADS, TJ, STAGES>());
     // f2 (MATH & 256): two-level FLOAT accumulation, the default.  A single float accumulator per lane is
     // not just noisy at large N, it is BIASED: summed over 5e5 terms the force magnitude comes out
     // systematically low (N = 1 M: -2e-5 here, -7e-5 for the reference's own single-accumulator float
     // loop, measured against fp64 -- tests/golden/truth_*), and the kinetic energy inherits twice that.
     // Folding the lane sums into a second float per (body, component) in shared memory after every 4th
     // j tile keeps every float sum <= 1024 terms long; cost: 12 LDS/FADD/STS per 24 576 FP32 instructions.
-    float *hif = reinterpret_cast<float *>(smem_raw + step_smem_bytes<THREADS, TJ, STAGES, 0, MATH & kMathQScale>());
+    float *hif = reinterpret_cast<float *>(smem_raw + step_smem_bytes<THREADS, TJ, STAGES>());
 
     const int tid = threadIdx.x;
 #ifdef NBX_TRACE
@@ -336,14 +328,6 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         const int head = min(cnt, p.n_pad - j0);
         const int st = t % STAGES;
         NBX_CHECK(cnt > 0 && (cnt & 7) == 0 && j0 >= 0 && j0 + head <= p.n_pad && (j0 & 7) == 0);
-        if (QS) {
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(p.qrec);
-            unsigned char *dst = smem_raw + st * (TJ * 24);
-            mbar_expect_tx(&full[st], (uint32_t)cnt * 24u);
-            tma_load_1d(dst, src + (size_t)j0 * 24, (uint32_t)head * 24u, &full[st]);
-            if (head < cnt) tma_load_1d(dst + head * 24, src, (uint32_t)(cnt - head) * 24u, &full[st]);
-            return;
-        }
         mbar_expect_tx(&full[st], (uint32_t)cnt * 16u);
         tma_load_1d(tiles + st * TJ, p.pos_in + j0, (uint32_t)head * 16u, &full[st]);
         if (head < cnt) tma_load_1d(tiles + st * TJ + head, p.pos_in, (uint32_t)(cnt - head) * 16u, &full[st]);
@@ -391,60 +375,12 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         const int st = t % STAGES;
         mbar_wait(&full[st], (t / STAGES) & 1);
         if (t == 0) NBX_STAMP(1);
-        const float4 *rec = QS ? reinterpret_cast<const float4 *>(smem_raw + st * (TJ * 24)) : tiles + st * TJ;
+        const float4 *rec = tiles + st * TJ;
         const int nrec = min(TJ, je - (jb + t * TJ)) >> 1;  // records in this tile (multiple of 4)
 #pragma unroll 1
         for (int jr = 0; jr < nrec; jr += UNROLL) {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                if (QS) {
-                    // q-scaled pair (11 packed FP32 instructions instead of 12).  With q_j = (G m_j)^(-1/2) the record
-                    // holds q r_j, q and q^2 eps; then
-                    //     e = q (r_j - r_i) = fma(-r_i, q, q r_j)                3 FFMA2 (were 3 FADD2)
-                    //     w = e.e + q^2 eps = q^2 (|d|^2 + eps)                  3 FFMA2
-                    //     u = rsqrt(w)^3    = (G m)^(3/2) (|d|^2 + eps)^(-3/2)   2 MUFU + 2 FMUL2 (were 3: no "times G m")
-                    //     a += u e          = G m (|d|^2 + eps)^(-3/2) d         3 FFMA2
-                    // q r_j is rounded once per body and step (half an ulp of the position); measured effect on the
-                    // force at N >= 262 144: none (tests/qscale_emulation.py); at N = 2000 it is 2e-7 instead of 2e-8,
-                    // which is why small shards keep the 12-instruction pair.
-                    const float4 *r3 = rec + 3 * (jr + u);
-                    const float4 qa = r3[0], qb = r3[1];
-                    const float2 qe = *reinterpret_cast<const float2 *>(r3 + 2);
-                    const float2 qx = make_float2(qa.x, qa.y), qy = make_float2(qa.z, qa.w);
-                    const float2 qz = make_float2(qb.x, qb.y), qq = make_float2(qb.z, qb.w);
-                    float2 ex[R], ey[R], ez[R], sv[R];
-                    constexpr int QP = (MATH >> 12) & 1023;     // source-order bits as in PERM below
-#pragma unroll
-                    for (int bb = 0; bb < R; ++bb) {
-                        const int b = (QP & 16) ? R - 1 - bb : bb;
-                        if (QP & 1) {
-                            ex[b] = __ffma2_rn(qq, nx[b], qx); ey[b] = __ffma2_rn(qq, ny[b], qy); ez[b] = __ffma2_rn(qq, nz[b], qz);
-                        } else {
-                            ex[b] = __ffma2_rn(nx[b], qq, qx); ey[b] = __ffma2_rn(ny[b], qq, qy); ez[b] = __ffma2_rn(nz[b], qq, qz);
-                        }
-                    }
-                    auto qv = [](int bit, int b) { return (QP & bit) ? R - 1 - b : b; };
-#pragma unroll
-                    for (int b = 0; b < R; ++b) sv[qv(32, b)] = __ffma2_rn(ex[qv(32, b)], ex[qv(32, b)], qe);
-#pragma unroll
-                    for (int b = 0; b < R; ++b) sv[qv(32, b)] = __ffma2_rn(ey[qv(32, b)], ey[qv(32, b)], sv[qv(32, b)]);
-#pragma unroll
-                    for (int b = 0; b < R; ++b) sv[qv(32, b)] = __ffma2_rn(ez[qv(32, b)], ez[qv(32, b)], sv[qv(32, b)]);
-#pragma unroll
-                    for (int b = 0; b < R; ++b) sv[qv(64, b)] = make_float2(rsqrt_approx(sv[qv(64, b)].x), rsqrt_approx(sv[qv(64, b)].y));
-#pragma unroll
-                    for (int b = 0; b < R; ++b) sv[qv(128, b)] = __fmul2_rn(__fmul2_rn(sv[qv(128, b)], sv[qv(128, b)]), sv[qv(128, b)]);
-#pragma unroll
-                    for (int bb = 0; bb < R; ++bb) {
-                        const int b = (QP & 8) ? R - 1 - bb : bb;
-                        if (QP & 256) {
-                            ax[b] = __ffma2_rn(sv[b], ex[b], ax[b]); ay[b] = __ffma2_rn(sv[b], ey[b], ay[b]); az[b] = __ffma2_rn(sv[b], ez[b], az[b]);
-                        } else {
-                            ax[b] = __ffma2_rn(ex[b], sv[b], ax[b]); ay[b] = __ffma2_rn(ey[b], sv[b], ay[b]); az[b] = __ffma2_rn(ez[b], sv[b], az[b]);
-                        }
-                    }
-                    continue;
-                }
                 const float4 q0 = rec[2 * (jr + u)];
                 const float4 q1 = rec[2 * (jr + u) + 1];
                 const float2 xj = make_float2(q0.x, q0.y), yj = make_float2(q0.z, q0.w);
@@ -766,56 +702,6 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                 if (g != p.rank) st_release_sys(&p.peer_flags[g][p.rank], epoch);
         }
     }
-}
-
-// ------------------------------------------------------------------------------
-//  q-scaled shapes: derive the j-records of the 11-instruction pair from the state records.
-//  One thread per body pair of the window [rec_org, rec_org + rec_len) (modulo n_pad / 2):
-//     {x0,x1,y0,y1 | z0,z1,Gm0,Gm1}  ->  {q x0,q x1,q y0,q y1 | q z0,q z1,q0,q1 | q0^2 eps,q1^2 eps,0,0},   q = Gm^(-1/2)
-//  Runs on the step's stream right before step_kernel (which still takes its i-bodies, the Euler update
-//  and the exchange from the state records): 40 bytes per body of HBM traffic, 20 us at N = 4 M against a
-//  step of 0.8 - 6.5 s.  Zero-mass bodies (padding) get Gm = 1e-30: q = 1e15, their pair term underflows to 0.
-//  In P2P mode this is the first kernel of a step to read what the peers stored, so it carries the same
-//  bounded wait for their flags as step_kernel (which then finds them set).
-// ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) qscale_kernel(const __grid_constant__ StepParams p, int rec_org, int rec_len)
-{
-    __shared__ int s_bad;
-    if (threadIdx.x == 0) {
-        int bad = p.p2p ? ld_volatile(p.dev_err) : 0;
-        if (p.p2p && !bad) {
-            const int epoch = *p.dev_epoch;
-            for (int g = 0; g < p.world && !bad; ++g) {
-                if (g == p.rank || ld_acquire_sys(&p.my_flags[g]) >= epoch) continue;
-                const unsigned long long t0 = globaltimer_ns();
-                while (ld_acquire_sys(&p.my_flags[g]) < epoch) {
-                    if ((bad = ld_volatile(p.dev_err)) != 0) break;
-                    if (globaltimer_ns() - t0 > p.peer_wait_ns) {
-                        dev_fail(p.dev_err, kDevErrPeerTimeout | (g << 8));
-                        bad = 1;
-                        break;
-                    }
-                    __nanosleep(200);
-                }
-            }
-        }
-        s_bad = bad;
-    }
-    __syncthreads();
-    if (s_bad) return;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rec_len) return;
-    const int nrec = p.n_pad >> 1;
-    int rec = rec_org + r;
-    if (rec >= nrec) rec -= nrec;
-    NBX_CHECK(p.qrec != nullptr && rec >= 0 && rec < nrec);
-    const float4 q0 = __ldcg(&p.pos_in[2 * rec]);
-    const float4 q1 = __ldcg(&p.pos_in[2 * rec + 1]);
-    const float s0 = 1.0f / sqrtf(fmaxf(q1.z, 1e-30f));
-    const float s1 = 1.0f / sqrtf(fmaxf(q1.w, 1e-30f));
-    p.qrec[3 * rec] = make_float4(s0 * q0.x, s1 * q0.y, s0 * q0.z, s1 * q0.w);
-    p.qrec[3 * rec + 1] = make_float4(s0 * q1.x, s1 * q1.y, s0, s1);
-    p.qrec[3 * rec + 2] = make_float4((s0 * s0) * p.eps2, (s1 * s1) * p.eps2, 0.f, 0.f);
 }
 
 // ------------------------------------------------------------------------------
