@@ -262,7 +262,7 @@ class Bench:
         dist.barrier(); torch.cuda.synchronize()
         if sampler:
             sampler.start()
-        launches0 = ctx.info()["kernel_launches"]
+        i0 = ctx.info()
         t0 = time.perf_counter()
         kernel_s, ke_last = 0.0, 0.0
         for _ in range(steps):
@@ -271,7 +271,10 @@ class Bench:
         torch.cuda.synchronize(); dist.barrier()
         wall = dist.reduce_scalar(time.perf_counter() - t0, "max")
         kernel_s = dist.reduce_scalar(kernel_s, "max")
-        self.timed_launches = ctx.info()["kernel_launches"] - launches0     # force-kernel launches in the timed region
+        i1 = ctx.info()      # launches in the timed region: the step kernel, and (q-scaled shapes) the record rewrite before it
+        self.timed_launches_detail = {"step_kernel": int(i1["kernel_launches"] - i0["kernel_launches"]),
+                                      "qscale_kernel": int(i1["aux_launches"] - i0["aux_launches"])}
+        self.timed_launches = sum(self.timed_launches_detail.values())
         return kernel_s, wall, ke_last
 
     # ---- parity of one workload on this set of GPUs (never inside a timed region)
@@ -469,7 +472,7 @@ def main():
     kernel_s, wall, ke_last = B.timed_steps(ctx, args.steps, args.warmup, sampler)
     clocks = sampler.stop()
     info1 = ctx.info()
-    launches = B.timed_launches
+    launches, launches_detail = B.timed_launches, dict(B.timed_launches_detail)
     pairs_per_step = float(n) * float(n)
     value, achieved_tflops, peak_tflops = B.rate_block(n, kernel_s, args.steps)
 
@@ -634,7 +637,7 @@ def main():
                      "hbm": {"algorithmic_bytes_per_launch": 64 * n // args.gpus, "achieved_gbs": round(64.0 * n / args.gpus / (kernel_s / args.steps) / 1e9, 2),
                              "peak_gbs": peaks.get("hbm_gbs"), "frac": round(64.0 * n / args.gpus / (kernel_s / args.steps) / 1e9 / peaks.get("hbm_gbs", 6650.0), 6)},
                      "note": "compute-bound on the FP32 pipe, not HBM or tensor: 12 FP32 lane-ops per pair, 6 of them FMAs, so 20 algorithmic flop/pair caps at 20/24 = 83.3% of the FMA peak; HBM need is 64 B/body/step"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "parity": parity,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_detail": launches_detail, "parity": parity,
     }
     if strong and world > 1 and wl_key == "c3":
         line["strong_efficiency"] = round(strong["ms_per_step"] / (world * ms_per_step), 4)

@@ -106,13 +106,14 @@ struct Variant {
     int r2, threads, tj, stages, unroll, minb;
     int smem;
     const void *fn;
+    bool qscale;   // j-records come from the q-scaled array (qscale_kernel runs before every step launch)
 };
 
 template <int R2, int THREADS, int TJ, int STAGES, int UNROLL, int MINB, int MATH = 0>
 static Variant make_variant(const char *name)
 {
     return Variant{name, R2, THREADS, TJ, STAGES, UNROLL, MINB, nbx::step_smem_bytes<THREADS, TJ, STAGES, R2, MATH>(),
-                   (const void *)nbx::step_kernel<R2, THREADS, TJ, STAGES, UNROLL, MINB, MATH>};
+                   (const void *)nbx::step_kernel<R2, THREADS, TJ, STAGES, UNROLL, MINB, MATH>, (MATH & nbx::kMathQScale) != 0};
 }
 
 static const std::vector<Variant> &variants()
@@ -134,7 +135,20 @@ static const std::vector<Variant> &variants()
         make_variant<2, 128, 256, 4, 2, 4>("r4_t128_u2"),
         make_variant<2, 512, 512, 4, 2, 1>("r4_t512_u2"),
         make_variant<2, 64, 128, 4, 2, 8>("r4_t64_u2"),
+        // "_qi": the q-scaled pair with lanes packed over i-bodies, 11 packed FP32 instructions instead of 12 (see the QS block in nbx_kernels.cuh)
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi"),   // [7]
 #ifdef NBX_ABLATION
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (1 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi_p1"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (256 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi_p256"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (257 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi_p257"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (488 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi_p488"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (489 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi_p489"),
+        make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | nbx::kMathQScale>("r4_t256_u2_stage_f2_qi"),
+        make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | (256 << 12) | nbx::kMathQScale>("r4_t256_u2_stage_f2_qi_p256"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | nbx::kMathQScale>("r4_t256_u4_stage_qi"),
+        make_variant<4, 128, 256, 4, 2, 4, 16 | 256 | 1024 | nbx::kMathQScale>("r8_t128_u2_stage_f2_qi"),
+        make_variant<4, 128, 256, 4, 2, 4, 16 | 256 | 1024 | (256 << 12) | nbx::kMathQScale>("r8_t128_u2_stage_f2_qi_p256"),
+        make_variant<4, 256, 256, 4, 2, 1, 16 | 256 | 1024 | nbx::kMathQScale>("r8_t256_u2_stage_f2_qi"),
         // Shapes kept only for the tuning tools (tools/sweep.py, tools/ab.py): `make ablation`
         // builds libnbx_ablation.so with them; the product library does not carry them.
         make_variant<2, 256, 256, 4, 2, 2>("r4_t256_u2"),
@@ -182,7 +196,15 @@ static const std::vector<Variant> &variants()
     return v;
 }
 
-constexpr int kLargeVariant = 0, kSmallVariant = 1, kAccurateVariant = 2;
+constexpr int kLargeVariant = 0, kSmallVariant = 1, kAccurateVariant = 2, kQScaleVariant = 7;
+// From this many bodies on the 11-instruction q-scaled pair is the default (its one extra rounding per body is
+// invisible in a sum over >= 65 536 pairs; below, the 12-instruction pair is kept: tests/qscale_emulation.py).
+constexpr int kQScaleMinBodies = 65536;
+#ifdef NBX_LARGE_QS
+constexpr bool kQScaleDefault = true;
+#else
+constexpr bool kQScaleDefault = false;
+#endif
 constexpr int kSmallShardBodies = 8192;   // below this the 256-body CTAs of kSmallVariant fill the SMs better
 
 // ------------------------------------------------------------------------------
@@ -198,6 +220,7 @@ struct nbx_ctx {
     float4 *pos[2] = {nullptr, nullptr};
     int cur = 0;
     float4 *vel = nullptr;
+    float4 *qrec = nullptr;    // q-scaled shapes only: 24 B per body, rewritten before every step launch
     float4 *part = nullptr;
     float4 *acc = nullptr;
     int *tile_ticket = nullptr;
@@ -247,6 +270,23 @@ struct nbx_ctx {
     double last_run_seconds = 0.0, kernel_seconds_total = 0.0;
 };
 
+// Validation builds (-DNBX_LARGE_QS -DNBX_ABLATION) may name the q-scaled shape to use: NBX_LARGE_VARIANT=<shape name>.
+static int qscale_default_variant()
+{
+#ifdef NBX_LARGE_QS
+    static const int v = [] {
+        const char *want = std::getenv("NBX_LARGE_VARIANT");
+        if (want)
+            for (size_t i = 0; i < variants().size(); ++i)
+                if (std::strcmp(want, variants()[i].name) == 0 && variants()[i].qscale) return (int)i;
+        return kQScaleVariant;
+    }();
+    return v;
+#else
+    return kQScaleVariant;
+#endif
+}
+
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // j-split count for `tiles` equal i-tiles sweeping `j_len` j-bodies on `sms` SMs (cost model below).
@@ -275,7 +315,9 @@ static Plan make_plan(int n_pad, int i_count, int world, int sm_count, int excha
     Plan p{};
     p.variant = opt_variant >= 0 ? opt_variant
                 : opt_accurate   ? kAccurateVariant
-                                 : (i_count < kSmallShardBodies ? kSmallVariant : kLargeVariant);
+                : i_count < kSmallShardBodies ? kSmallVariant
+                : (kQScaleDefault && n_pad >= kQScaleMinBodies) ? qscale_default_variant()
+                                                                : kLargeVariant;
     const Variant &v = variants()[p.variant];
     const int bi = v.threads * v.r2 * 2;
     p.i_tiles = (i_count + bi - 1) / bi;
@@ -350,6 +392,8 @@ static int resolve(nbx_ctx *c)
     c->ctas_per_sm = occ;
 
     if (c->part) { CU(cudaFree(c->part)); c->part = nullptr; }
+    if (c->qrec) { CU(cudaFree(c->qrec)); c->qrec = nullptr; }
+    if (v.qscale) CU(cudaMalloc(&c->qrec, (size_t)c->n_pad * 24));
     if (c->tile_ticket) { CU(cudaFree(c->tile_ticket)); c->tile_ticket = nullptr; }
     if (c->ke_part) { CU(cudaFree(c->ke_part)); c->ke_part = nullptr; }
     if (splits > 1) CU(cudaMalloc(&c->part, (size_t)splits * c->split_bodies * sizeof(float4)));
@@ -376,6 +420,7 @@ static void fill_params(const nbx_ctx *c, StepParams &p, int in_buf, float4 *acc
     std::memset(&p, 0, sizeof p);
     p.pos_in = c->pos[in_buf];
     p.pos_out = c->pos[in_buf ^ 1];
+    p.qrec = c->qrec;
     p.vel = c->vel;
     p.part = c->part;
     p.tile_ticket = c->tile_ticket;
@@ -434,6 +479,13 @@ static int launch_step(nbx_ctx *c, int in_buf, float4 *acc_out = nullptr, int ph
     StepParams p;
     fill_params(c, p, in_buf, acc_out, phase);
     void *args[] = {&p};
+    if (v.qscale) {
+        // the launch's j window, in records; a plain launch: it starts when the previous step has completed
+        const int rec_org = p.j_org >> 1, rec_len = p.j_len >> 1;
+        nbx::qscale_kernel<<<(rec_len + 255) / 256, 256, 0, c->stream>>>(p, rec_org, rec_len);
+        CU(cudaGetLastError());
+        c->aux_launches++;
+    }
     const int ctas = c->whole_tiles + (c->i_tiles - c->whole_tiles) * p.j_splits;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
@@ -456,12 +508,13 @@ static int launch_step(nbx_ctx *c, int in_buf, float4 *acc_out = nullptr, int ph
 static int build_graph(nbx_ctx *c, int steps, cudaGraphExec_t *out)
 {
     cudaGraph_t g = nullptr;
-    const long long before = c->kernel_launches;
+    const long long before = c->kernel_launches, before_aux = c->aux_launches;
     CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     int rc = NBX_OK;
     for (int s = 0; s < steps && rc == NBX_OK; ++s) rc = launch_step(c, s & 1);
     cudaError_t e = cudaStreamEndCapture(c->stream, &g);
     c->kernel_launches = before;   // capturing is not launching
+    c->aux_launches = before_aux;
     if (rc != NBX_OK) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(NBX_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
     e = cudaGraphInstantiate(out, g, 0);
@@ -562,12 +615,14 @@ static int enqueue_steps(nbx_ctx *c, int nsteps)
         while (left >= 16) {
             CU(cudaGraphLaunch(c->graph16, c->stream));
             c->kernel_launches += 16;
+            if (variants()[c->variant].qscale) c->aux_launches += 16;
             left -= 16;
         }
         if (left >= 2 && !c->graph2) { int rc = build_graph(c, 2, &c->graph2); if (rc) return rc; }
         while (left >= 2) {
             CU(cudaGraphLaunch(c->graph2, c->stream));
             c->kernel_launches += 2;
+            if (variants()[c->variant].qscale) c->aux_launches += 2;
             left -= 2;
         }
     }
@@ -698,7 +753,7 @@ void nbx_destroy(nbx_ctx *c)
         cudaFree(c->pos[0]); cudaFree(c->pos[1]);
     }
     cudaFree(c->retired_pos[0]); cudaFree(c->retired_pos[1]);
-    cudaFree(c->vel); cudaFree(c->part); cudaFree(c->acc);
+    cudaFree(c->vel); cudaFree(c->qrec); cudaFree(c->part); cudaFree(c->acc);
     cudaFree(c->tile_ticket); cudaFree(c->ke_part); cudaFree(c->counters); cudaFree(c->flags);
     cudaFree(c->ke_dev); cudaFree(c->stage); cudaFree(c->trace);
     if (c->ev0) cudaEventDestroy(c->ev0);

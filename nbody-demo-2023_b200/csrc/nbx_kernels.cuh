@@ -75,7 +75,11 @@ struct StepParams {
     // Trace build (-DNBX_TRACE, libnbx_trace.so) only: per-CTA %globaltimer stamps, kTraceWords per CTA per step
     unsigned long long *trace;
     int trace_steps;                  // steps the buffer holds (later steps are not recorded)
+    // q-scaled shapes (MATH bit kMathQScale) only: the j-records in the form the 11-instruction pair needs,
+    // 48 bytes per body pair, rewritten from pos_in by qscale_kernel before every step launch
+    float4 *qrec;
 };
+constexpr int kMathQScale = 1 << 22;
 constexpr int kTraceWords = 6;        // start, first tile landed, sweep done, exit, smid, last-arriver flag
 
 // Values of *dev_err (low byte; the rest carries detail: peer rank << 8, or source line << 8).
@@ -197,11 +201,13 @@ template <bool SCALAR> __device__ __forceinline__ float2 fma2(float2 a, float2 b
 }
 
 // Shared-memory footprint of one CTA (host uses the same formula).  MATH bit 32 ("acc64") adds
-// one double per (i-body, component) per thread: the second accumulation level.
+// one double per (i-body, component) per thread: the second accumulation level; q-scaled shapes
+// stream 24 instead of 16 bytes per j-body.
 template <int THREADS, int TJ, int STAGES, int R2 = 0, int MATH = 0>
 __host__ __device__ constexpr int step_smem_bytes()
 {
-    return STAGES * TJ * 16 + 2 * STAGES * 8 + (THREADS / 32) * 8 + 16 + ((MATH & 32) ? 3 * 2 * R2 * THREADS * 8 : 0) +
+    return STAGES * TJ * ((MATH & kMathQScale) ? 24 : 16) + 2 * STAGES * 8 + (THREADS / 32) * 8 + 16 +
+           ((MATH & 32) ? 3 * 2 * R2 * THREADS * 8 : 0) +
            ((MATH & 256) ? 3 * 2 * R2 * THREADS * 4 : 0);
 }
 
@@ -224,7 +230,9 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + STAGES * TJ * 16);
+    constexpr bool QS = (MATH & kMathQScale) != 0;
+    constexpr int JB = QS ? 24 : 16;                         // bytes per j-body in the ring
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + STAGES * TJ * JB);
     uint64_t *empty = full + STAGES;
     double *red = reinterpret_cast<double *>(empty + STAGES);
     int *s_flag = reinterpret_cast<int *>(red + WARPS);
@@ -232,14 +240,14 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     // a double per (body, component) after every 4th j tile, so no float sum is longer than 2*TJ terms:
     // the large-N float summation error (1e-4 at 1 M, 1e-3 at 4 M for the reference's single
     // accumulator) drops to the 1e-6 level for ~1% time.  hi[q * THREADS + tid]: conflict-free.
-    double *hi = reinterpret_cast<double *>(smem_raw + step_smem_bytes<THREADS, TJ, STAGES>());
+    double *hi = reinterpret_cast<double *>(smem_raw + step_smem_bytes<THREADS, TJ, STAGES, 0, MATH & kMathQScale>());
     // f2 (MATH & 256): two-level FLOAT accumulation, the default.  A single float accumulator per lane is
     // not just noisy at large N, it is BIASED: summed over 5e5 terms the force magnitude comes out
     // systematically low (N = 1 M: -2e-5 here, -7e-5 for the reference's own single-accumulator float
     // loop, measured against fp64 -- tests/golden/truth_*), and the kinetic energy inherits twice that.
     // Folding the lane sums into a second float per (body, component) in shared memory after every 4th
     // j tile keeps every float sum <= 1024 terms long; cost: 12 LDS/FADD/STS per 24 576 FP32 instructions.
-    float *hif = reinterpret_cast<float *>(smem_raw + step_smem_bytes<THREADS, TJ, STAGES>());
+    float *hif = reinterpret_cast<float *>(smem_raw + step_smem_bytes<THREADS, TJ, STAGES, 0, MATH & kMathQScale>());
 
     const int tid = threadIdx.x;
 #ifdef NBX_TRACE
@@ -328,6 +336,14 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         const int head = min(cnt, p.n_pad - j0);
         const int st = t % STAGES;
         NBX_CHECK(cnt > 0 && (cnt & 7) == 0 && j0 >= 0 && j0 + head <= p.n_pad && (j0 & 7) == 0);
+        if (QS) {
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(p.qrec);
+            unsigned char *dst = smem_raw + st * (TJ * 24);
+            mbar_expect_tx(&full[st], (uint32_t)cnt * 24u);
+            tma_load_1d(dst, src + (size_t)j0 * 24, (uint32_t)head * 24u, &full[st]);
+            if (head < cnt) tma_load_1d(dst + head * 24, src, (uint32_t)(cnt - head) * 24u, &full[st]);
+            return;
+        }
         mbar_expect_tx(&full[st], (uint32_t)cnt * 16u);
         tma_load_1d(tiles + st * TJ, p.pos_in + j0, (uint32_t)head * 16u, &full[st]);
         if (head < cnt) tma_load_1d(tiles + st * TJ + head, p.pos_in, (uint32_t)(cnt - head) * 16u, &full[st]);
@@ -352,6 +368,10 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         NBX_CHECK(ip >= 0 && 2 * gp + 1 < (size_t)p.n_pad);
         const float4 q0 = __ldcg(&p.pos_in[2 * gp]);
         const float4 q1 = __ldcg(&p.pos_in[2 * gp + 1]);
+        if (QS) {   // lanes = the two bodies of the record
+            nx[k] = make_float2(-q0.x, -q0.y); ny[k] = make_float2(-q0.z, -q0.w); nz[k] = make_float2(-q1.x, -q1.y);
+            continue;
+        }
         nx[2 * k] = make_float2(-q0.x, -q0.x); nx[2 * k + 1] = make_float2(-q0.y, -q0.y);
         ny[2 * k] = make_float2(-q0.z, -q0.z); ny[2 * k + 1] = make_float2(-q0.w, -q0.w);
         nz[2 * k] = make_float2(-q1.x, -q1.x); nz[2 * k + 1] = make_float2(-q1.y, -q1.y);
@@ -375,12 +395,66 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         const int st = t % STAGES;
         mbar_wait(&full[st], (t / STAGES) & 1);
         if (t == 0) NBX_STAMP(1);
-        const float4 *rec = tiles + st * TJ;
+        const float4 *rec = QS ? reinterpret_cast<const float4 *>(smem_raw + st * (TJ * 24)) : tiles + st * TJ;
         const int nrec = min(TJ, je - (jb + t * TJ)) >> 1;  // records in this tile (multiple of 4)
 #pragma unroll 1
         for (int jr = 0; jr < nrec; jr += UNROLL) {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
+                if (QS) {
+                    // q-scaled pair, lanes packed over i-bodies (11 packed FP32 instructions instead of 12, and only
+                    // the three accumulates read three distinct 64-bit registers).  With q_j = (G m_j)^(-1/2) the
+                    // j-record holds the scalars q x_j, q, q y_j, q^2 eps, q z_j; per (i-pair, j):
+                    //     e = q (r_j - r_i) = fma(-r_i, q, q r_j)                3 FFMA2: a pair and two 32-bit scalars of
+                    //                                                            opposite register parity = 2 + 2 bank reads
+                    //     w = e.e + q^2 eps = q^2 (|d|^2 + eps)                  3 FFMA2
+                    //     u = rsqrt(w)^3    = (G m)^(3/2) (|d|^2 + eps)^(-3/2)   2 MUFU + 2 FMUL2 (no "times G m")
+                    //     a += u e          = G m (|d|^2 + eps)^(-3/2) d         3 FFMA2
+                    // Record pair = 48 bytes = {qx0,q0,qy0,qe0 | qz0,-,qx1,q1 | qy1,qe1,qz1,-}: in every LDS.128 the
+                    // q of a body sits in an odd register and its coordinates in even ones.
+                    const float4 *r3 = rec + 3 * (jr + u);
+                    const float4 c0 = r3[0], c1 = r3[1], c2 = r3[2];
+                    constexpr int QP = (MATH >> 12) & 1023;     // source-order bits
+                    constexpr int NU = 2 * R2;                  // (i-pair, j-body) units per record
+                    float2 ex[NU], ey[NU], ez[NU], sv[NU];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float sq = h ? c1.w : c0.y, sx = h ? c1.z : c0.x, sy = h ? c2.x : c0.z, sz = h ? c2.z : c1.x;
+                        const float2 qq = make_float2(sq, sq), qx = make_float2(sx, sx), qy = make_float2(sy, sy), qz = make_float2(sz, sz);
+#pragma unroll
+                        for (int k = 0; k < R2; ++k) {
+                            const int n = (QP & 1) ? k * 2 + h : h * R2 + k;
+                            ex[n] = __ffma2_rn(nx[k], qq, qx); ey[n] = __ffma2_rn(ny[k], qq, qy); ez[n] = __ffma2_rn(nz[k], qq, qz);
+                        }
+                    }
+                    auto body_of = [](int n) { return (QP & 1) ? (n & 1) : n / R2; };
+                    auto pair_of = [](int n) { return (QP & 1) ? (n >> 1) : n % R2; };
+                    auto ord = [](int bit, int n) { return (QP & bit) ? NU - 1 - n : n; };
+#pragma unroll
+                    for (int i = 0; i < NU; ++i) {
+                        const int n = ord(32, i);
+                        const float se = body_of(n) ? c2.y : c0.w;
+                        sv[n] = __ffma2_rn(ex[n], ex[n], make_float2(se, se));
+                    }
+#pragma unroll
+                    for (int i = 0; i < NU; ++i) sv[ord(32, i)] = __ffma2_rn(ey[ord(32, i)], ey[ord(32, i)], sv[ord(32, i)]);
+#pragma unroll
+                    for (int i = 0; i < NU; ++i) sv[ord(32, i)] = __ffma2_rn(ez[ord(32, i)], ez[ord(32, i)], sv[ord(32, i)]);
+#pragma unroll
+                    for (int i = 0; i < NU; ++i) sv[ord(64, i)] = make_float2(rsqrt_approx(sv[ord(64, i)].x), rsqrt_approx(sv[ord(64, i)].y));
+#pragma unroll
+                    for (int i = 0; i < NU; ++i) sv[ord(128, i)] = __fmul2_rn(__fmul2_rn(sv[ord(128, i)], sv[ord(128, i)]), sv[ord(128, i)]);
+#pragma unroll
+                    for (int i = 0; i < NU; ++i) {
+                        const int n = ord(8, i), k = pair_of(n);
+                        if (QP & 256) {
+                            ax[k] = __ffma2_rn(sv[n], ex[n], ax[k]); ay[k] = __ffma2_rn(sv[n], ey[n], ay[k]); az[k] = __ffma2_rn(sv[n], ez[n], az[k]);
+                        } else {
+                            ax[k] = __ffma2_rn(ex[n], sv[n], ax[k]); ay[k] = __ffma2_rn(ey[n], sv[n], ay[k]); az[k] = __ffma2_rn(ez[n], sv[n], az[k]);
+                        }
+                    }
+                    continue;
+                }
                 const float4 q0 = rec[2 * (jr + u)];
                 const float4 q1 = rec[2 * (jr + u) + 1];
                 const float2 xj = make_float2(q0.x, q0.y), yj = make_float2(q0.z, q0.w);
@@ -498,7 +572,20 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
             }
         }
         constexpr int FOLD = 4 << (2 * ((MATH >> 9) & 3));     // fold period in j tiles: 4 (default), 16, 64, 256
-        if ((MATH & 256) && ((t & (FOLD - 1)) == FOLD - 1 || t == ntiles - 1)) {
+        if (QS && (MATH & 256) && ((t & (FOLD - 1)) == FOLD - 1 || t == ntiles - 1)) {
+            // lanes are bodies: accumulator pair k holds bodies 2k (x lane) and 2k + 1 (y lane)
+#pragma unroll
+            for (int k = 0; k < R2; ++k) {
+                float *h0 = hif + (3 * (2 * k)) * THREADS + tid, *h1 = hif + (3 * (2 * k + 1)) * THREADS + tid;
+                const bool first = (t < FOLD);
+                h0[0] = (first ? 0.f : h0[0]) + ax[k].x; h0[THREADS] = (first ? 0.f : h0[THREADS]) + ay[k].x;
+                h0[2 * THREADS] = (first ? 0.f : h0[2 * THREADS]) + az[k].x;
+                h1[0] = (first ? 0.f : h1[0]) + ax[k].y; h1[THREADS] = (first ? 0.f : h1[THREADS]) + ay[k].y;
+                h1[2 * THREADS] = (first ? 0.f : h1[2 * THREADS]) + az[k].y;
+                ax[k] = ay[k] = az[k] = make_float2(0.f, 0.f);
+            }
+        }
+        if (!QS && (MATH & 256) && ((t & (FOLD - 1)) == FOLD - 1 || t == ntiles - 1)) {
 #pragma unroll
             for (int b = 0; b < R; ++b) {
                 float *h = hif + (3 * b) * THREADS + tid;
@@ -516,6 +603,26 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     NBX_STAMP(2);
     // ---- fold the two j lanes
     float fx[R], fy[R], fz[R];
+    if (QS) {
+        static_assert(!QS || !(MATH & (32 | 128)), "q-scaled shapes: float accumulation only");
+        // back to the per-body view the split combine and the epilogue use
+#pragma unroll
+        for (int k = R2 - 1; k >= 0; --k) {
+            const float2 tx = nx[k], ty = ny[k], tz = nz[k];
+            nx[2 * k] = make_float2(tx.x, tx.x); nx[2 * k + 1] = make_float2(tx.y, tx.y);
+            ny[2 * k] = make_float2(ty.x, ty.x); ny[2 * k + 1] = make_float2(ty.y, ty.y);
+            nz[2 * k] = make_float2(tz.x, tz.x); nz[2 * k + 1] = make_float2(tz.y, tz.y);
+        }
+        if (!(MATH & 256)) {
+#pragma unroll
+            for (int k = R2 - 1; k >= 0; --k) {
+                const float2 tx = ax[k], ty = ay[k], tz = az[k];
+                ax[2 * k] = make_float2(tx.x, 0.f); ax[2 * k + 1] = make_float2(tx.y, 0.f);
+                ay[2 * k] = make_float2(ty.x, 0.f); ay[2 * k + 1] = make_float2(ty.y, 0.f);
+                az[2 * k] = make_float2(tz.x, 0.f); az[2 * k + 1] = make_float2(tz.y, 0.f);
+            }
+        }
+    }
 #pragma unroll
     for (int b = 0; b < R; ++b) {
         if (MATH & 32) {
@@ -702,6 +809,56 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                 if (g != p.rank) st_release_sys(&p.peer_flags[g][p.rank], epoch);
         }
     }
+}
+
+// ------------------------------------------------------------------------------
+//  q-scaled shapes: derive the j-records of the 11-instruction pair from the state records.
+//  One thread per body pair of the window [rec_org, rec_org + rec_len) (modulo n_pad / 2):
+//     {x0,x1,y0,y1 | z0,z1,Gm0,Gm1}  ->  {q0 x0,q0,q0 y0,q0^2 eps | q0 z0,0,q1 x1,q1 | q1 y1,q1^2 eps,q1 z1,0},   q = Gm^(-1/2)
+//  Runs on the step's stream right before step_kernel (which still takes its i-bodies, the Euler update
+//  and the exchange from the state records): 40 bytes per body of HBM traffic, 20 us at N = 4 M against a
+//  step of 0.8 - 6.5 s.  Zero-mass bodies (padding) get Gm = 1e-30: q = 1e15, their pair term underflows to 0.
+//  In P2P mode this is the first kernel of a step to read what the peers stored, so it carries the same
+//  bounded wait for their flags as step_kernel (which then finds them set).
+// ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qscale_kernel(const __grid_constant__ StepParams p, int rec_org, int rec_len)
+{
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) {
+        int bad = p.p2p ? ld_volatile(p.dev_err) : 0;
+        if (p.p2p && !bad) {
+            const int epoch = *p.dev_epoch;
+            for (int g = 0; g < p.world && !bad; ++g) {
+                if (g == p.rank || ld_acquire_sys(&p.my_flags[g]) >= epoch) continue;
+                const unsigned long long t0 = globaltimer_ns();
+                while (ld_acquire_sys(&p.my_flags[g]) < epoch) {
+                    if ((bad = ld_volatile(p.dev_err)) != 0) break;
+                    if (globaltimer_ns() - t0 > p.peer_wait_ns) {
+                        dev_fail(p.dev_err, kDevErrPeerTimeout | (g << 8));
+                        bad = 1;
+                        break;
+                    }
+                    __nanosleep(200);
+                }
+            }
+        }
+        s_bad = bad;
+    }
+    __syncthreads();
+    if (s_bad) return;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rec_len) return;
+    const int nrec = p.n_pad >> 1;
+    int rec = rec_org + r;
+    if (rec >= nrec) rec -= nrec;
+    NBX_CHECK(p.qrec != nullptr && rec >= 0 && rec < nrec);
+    const float4 q0 = __ldcg(&p.pos_in[2 * rec]);
+    const float4 q1 = __ldcg(&p.pos_in[2 * rec + 1]);
+    const float s0 = 1.0f / sqrtf(fmaxf(q1.z, 1e-30f));
+    const float s1 = 1.0f / sqrtf(fmaxf(q1.w, 1e-30f));
+    p.qrec[3 * rec] = make_float4(s0 * q0.x, s0, s0 * q0.z, (s0 * s0) * p.eps2);
+    p.qrec[3 * rec + 1] = make_float4(s0 * q1.x, 0.f, s1 * q0.y, s1);
+    p.qrec[3 * rec + 2] = make_float4(s1 * q0.w, (s1 * s1) * p.eps2, s1 * q1.y, 0.f);
 }
 
 // ------------------------------------------------------------------------------

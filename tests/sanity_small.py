@@ -32,7 +32,9 @@ def main():
         arrs = nbx.ic(n)
         for opts in ({}, {"j_splits": 1}, {"j_splits": 3}, {"j_splits": 61, "graph": 1}, {"graph": 0, "pdl": 1},
                      {"accurate": 1}, {"variant": names.index("r4_t128_u2")}, {"variant": names.index("r4_t512_u2")},
-                     {"variant": names.index("r4_t64_u2"), "j_splits": 5}):
+                     {"variant": names.index("r4_t64_u2"), "j_splits": 5},
+                     {"variant": names.index("r4_t256_u4_stage_f2_qi")},
+                     {"variant": names.index("r4_t256_u4_stage_f2_qi"), "j_splits": 3, "graph": 1}):
             with nbx.Context(n) as c:
                 for k, v in opts.items():
                     c.set_option(k, v)

@@ -155,7 +155,7 @@ def test_launch_plan_host_logic(nbx):
     assert names[c0["variant"]] == "r2_t128_u4" and c0["i_tiles"] == 8 and c0["whole_tiles"] == 0 and c0["j_splits"] > 1
     assert c0["use_graph"] == 1 and c0["n_pad"] == 2000
     c1 = nbx.plan(16384)
-    assert len(names) == 7, "ablation shapes must not ship in the product library"
+    assert len(names) == 8, "ablation shapes must not ship in the product library"
     assert names[c1["variant"]] == "r4_t256_u4_stage_f2" and (c1["i_tiles"], c1["whole_tiles"], c1["j_splits"]) == (16, 0, 9)
     assert c1["use_graph"] == 1
     c2 = nbx.plan(1 << 20)

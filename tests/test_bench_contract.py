@@ -43,7 +43,7 @@ def test_native_arm_line():
     d = _run(["--steps", "1", "--warmup", "3", "--no-cpu-baseline", "--no-extras"])
     assert (COMMON - {"cpu_baseline"}) <= set(d) and "impl" not in d
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 3 and d["dtype"] == "f32"
-    assert d["gpu_launches"] == 1
+    assert d["gpu_launches_detail"]["step_kernel"] == 1 and d["gpu_launches"] == 1 + d["gpu_launches_detail"]["qscale_kernel"]
     rf = d["roofline"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf)
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-3 and 0.5 < rf["frac"] < 0.84

@@ -211,6 +211,39 @@ def test_accelerations_vs_fp64_truth(nbx, oracle):
     assert np.max(err) < 1e-4 and np.median(err) < 5e-6
 
 
+def test_qscaled_pair_vs_oracle(nbx, oracle):
+    """The 11-instruction q-scaled pair (shape "_qi": j-records pre-multiplied by (G m_j)^(-1/2), rewritten by
+    qscale_kernel before every step) forced at sizes where it is not the default: ragged N with zero-mass
+    padding, j-split + graph replay, a real body of mass zero, and sampled forces against the fp64 truth."""
+    qs = nbx.variant_names().index("r4_t256_u4_stage_f2_qi")
+    n = 20011
+    s = oracle.ic_uniform(n)
+    arrs = list(nbx.ic(n))
+    arrs[6] = arrs[6].copy()
+    arrs[6][[5, 777, n - 1]] = 0.0                    # massless bodies: feel forces, exert none
+    s.mass[[5, 777, n - 1]] = 0.0
+    ke_o = oracle.run(s, 6, variant="ver7")
+    for opts in (dict(), dict(j_splits=5, graph=1), dict(j_splits=1, pdl=1)):
+        ke, out, info = gpu_run(nbx, arrs, 6, variant=qs, **opts)
+        assert info["aux_launches"] >= 6                # one qscale launch per step
+        assert np.all(np.isfinite(ke)) and np.max(np.abs(ke - ke_o) / ke_o) < KE_TOL, opts
+        assert rel_l2(np.stack(out[:3], axis=1), s.pos()) < POS_TOL, opts
+    n = 65536
+    arrs = nbx.ic(n)
+    s = oracle.ic_uniform(n)
+    sel = np.random.default_rng(1).choice(n, 2048, replace=False).astype(np.int32)
+    truth = oracle.acc_fp64(s, sel)
+    errs = {}
+    for name, v in (("12-instruction", 0), ("q-scaled", qs)):
+        with nbx.Context(n) as c:
+            c.set_option("variant", v)
+            c.upload(*arrs)
+            acc = c.accelerations()
+        errs[name] = np.linalg.norm(acc[sel] - truth, axis=1) / np.linalg.norm(truth, axis=1)
+        print(f"\nN=65536 sampled forces vs fp64, {name}: median {np.median(errs[name]):.2e} max {errs[name].max():.2e}")
+    assert np.max(errs["q-scaled"]) < 1e-5 and np.median(errs["q-scaled"]) < 2e-6
+
+
 def test_i_sharding_is_exact_on_one_gpu(nbx):
     # the multi-GPU decomposition: rank r of W computes the i-shard [r*N/W, (r+1)*N/W) against
     # all j.  With the same j-split the per-body sums are the same instructions in the same
