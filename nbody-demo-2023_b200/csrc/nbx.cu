@@ -127,7 +127,7 @@ static const std::vector<Variant> &variants()
         // (504 << 12): the four bodies are walked in reverse order in every stage of the loop body and the accumulate
         // takes its multiplicands as (s, d) -- the fastest of 58 semantically equivalent source orders on the final
         // source (ptxas register assignment / operand slots; profiles/r02_ab_perm_*)
-        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (504 << 12)>("r4_t256_u4_stage_f2"),   // [0] default for large shards (kLargeVariant)
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (504 << 12)>("r4_t256_u4_stage_f2"),   // [0] default for shards >= 8192 bodies of N < 65 536 (kLargeVariant)
         make_variant<1, 128, 256, 4, 4, 6>("r2_t128_u4"),                            // [1] default for small shards (kSmallVariant)
         make_variant<2, 256, 256, 4, 4, 2, 48>("r4_t256_u4_stage_acc64"),            // [2] accuracy option (kAccurateVariant)
         make_variant<2, 256, 256, 4, 4, 2, 16>("r4_t256_u4_stage"),                  // [3] one float accumulator per lane, like the reference's loops
@@ -135,20 +135,22 @@ static const std::vector<Variant> &variants()
         make_variant<2, 128, 256, 4, 2, 4>("r4_t128_u2"),
         make_variant<2, 512, 512, 4, 2, 1>("r4_t512_u2"),
         make_variant<2, 64, 128, 4, 2, 8>("r4_t64_u2"),
-        // "_qi": the q-scaled pair with lanes packed over i-bodies, 11 packed FP32 instructions instead of 12 (see the QS block in nbx_kernels.cuh)
-        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi"),   // [7]
+        // "_qi": the q-scaled pair with lanes packed over i-bodies -- 11 packed FP32 instructions instead of 12, and the
+        // subtract reads a register pair and two scalars of opposite parity (QS block in nbx_kernels.cuh); source order 1
+        // (units numbered pair-major) is the fastest of the 7 orders A/B-ed (profiles/r02_ab_qscaled_ipacked_*.log)
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (1 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi"),   // [7] default from 65 536 bodies on (kQScaleVariant)
 #ifdef NBX_ABLATION
-        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (1 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi_p1"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi_p0"),
         make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (256 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi_p256"),
         make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (257 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi_p257"),
         make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (488 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi_p488"),
         make_variant<2, 256, 256, 4, 4, 2, 16 | 256 | 1024 | (489 << 12) | nbx::kMathQScale>("r4_t256_u4_stage_f2_qi_p489"),
-        make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | nbx::kMathQScale>("r4_t256_u2_stage_f2_qi"),
+        make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | nbx::kMathQScale>("r4_t256_u2_stage_f2_qi_p0"),
         make_variant<2, 256, 256, 4, 2, 2, 16 | 256 | 1024 | (256 << 12) | nbx::kMathQScale>("r4_t256_u2_stage_f2_qi_p256"),
-        make_variant<2, 256, 256, 4, 4, 2, 16 | nbx::kMathQScale>("r4_t256_u4_stage_qi"),
-        make_variant<4, 128, 256, 4, 2, 4, 16 | 256 | 1024 | nbx::kMathQScale>("r8_t128_u2_stage_f2_qi"),
+        make_variant<2, 256, 256, 4, 4, 2, 16 | nbx::kMathQScale>("r4_t256_u4_stage_qi_p0"),                      // one float accumulator per body
+        make_variant<4, 128, 256, 4, 2, 4, 16 | 256 | 1024 | nbx::kMathQScale>("r8_t128_u2_stage_f2_qi_p0"),      // 8 bodies per thread: same speed
         make_variant<4, 128, 256, 4, 2, 4, 16 | 256 | 1024 | (256 << 12) | nbx::kMathQScale>("r8_t128_u2_stage_f2_qi_p256"),
-        make_variant<4, 256, 256, 4, 2, 1, 16 | 256 | 1024 | nbx::kMathQScale>("r8_t256_u2_stage_f2_qi"),
+        make_variant<4, 256, 256, 4, 2, 1, 16 | 256 | 1024 | nbx::kMathQScale>("r8_t256_u2_stage_f2_qi_p0"),
         // Shapes kept only for the tuning tools (tools/sweep.py, tools/ab.py): `make ablation`
         // builds libnbx_ablation.so with them; the product library does not carry them.
         make_variant<2, 256, 256, 4, 2, 2>("r4_t256_u2"),
@@ -197,14 +199,10 @@ static const std::vector<Variant> &variants()
 }
 
 constexpr int kLargeVariant = 0, kSmallVariant = 1, kAccurateVariant = 2, kQScaleVariant = 7;
-// From this many bodies on the 11-instruction q-scaled pair is the default (its one extra rounding per body is
-// invisible in a sum over >= 65 536 pairs; below, the 12-instruction pair is kept: tests/qscale_emulation.py).
+// From this many bodies on, the 11-instruction q-scaled pair is the default: +2.9 % at N = 1 M, +1.5 % at 65 536, slower at
+// 16 384 (its record rewrite is one more launch per step); its one extra rounding per body is invisible in a sum over
+// >= 65 536 pairs and 2e-7 instead of 2e-8 of the force at N = 2000 (tests/qscale_emulation.py).
 constexpr int kQScaleMinBodies = 65536;
-#ifdef NBX_LARGE_QS
-constexpr bool kQScaleDefault = true;
-#else
-constexpr bool kQScaleDefault = false;
-#endif
 constexpr int kSmallShardBodies = 8192;   // below this the 256-body CTAs of kSmallVariant fill the SMs better
 
 // ------------------------------------------------------------------------------
@@ -270,23 +268,6 @@ struct nbx_ctx {
     double last_run_seconds = 0.0, kernel_seconds_total = 0.0;
 };
 
-// Validation builds (-DNBX_LARGE_QS -DNBX_ABLATION) may name the q-scaled shape to use: NBX_LARGE_VARIANT=<shape name>.
-static int qscale_default_variant()
-{
-#ifdef NBX_LARGE_QS
-    static const int v = [] {
-        const char *want = std::getenv("NBX_LARGE_VARIANT");
-        if (want)
-            for (size_t i = 0; i < variants().size(); ++i)
-                if (std::strcmp(want, variants()[i].name) == 0 && variants()[i].qscale) return (int)i;
-        return kQScaleVariant;
-    }();
-    return v;
-#else
-    return kQScaleVariant;
-#endif
-}
-
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // j-split count for `tiles` equal i-tiles sweeping `j_len` j-bodies on `sms` SMs (cost model below).
@@ -316,8 +297,8 @@ static Plan make_plan(int n_pad, int i_count, int world, int sm_count, int excha
     p.variant = opt_variant >= 0 ? opt_variant
                 : opt_accurate   ? kAccurateVariant
                 : i_count < kSmallShardBodies ? kSmallVariant
-                : (kQScaleDefault && n_pad >= kQScaleMinBodies) ? qscale_default_variant()
-                                                                : kLargeVariant;
+                : n_pad >= kQScaleMinBodies   ? kQScaleVariant
+                                              : kLargeVariant;
     const Variant &v = variants()[p.variant];
     const int bi = v.threads * v.r2 * 2;
     p.i_tiles = (i_count + bi - 1) / bi;

@@ -125,7 +125,9 @@ void GSimulation::start()
     int forced_variant = -1;
     if (_thread_dim0 != 0) {   // cuda/Compute.cu:137-145: block size from thread_dim0
         const int want = _thread_dim0 >= 512 ? 512 : _thread_dim0 >= 256 ? 256 : _thread_dim0 >= 128 ? 128 : 64;
-        const std::string name = want == 256 ? std::string("r4_t256_u4_stage_f2") : "r4_t" + std::to_string(want) + "_u2";
+        // 256 threads: the library's own 256-thread shape for this N (the q-scaled one from 65 536 bodies on)
+        const std::string name = want == 256 ? std::string(n >= 65536 ? "r4_t256_u4_stage_f2_qi" : "r4_t256_u4_stage_f2")
+                                             : "r4_t" + std::to_string(want) + "_u2";
         for (int v = 0; v < nbx_variant_count(); ++v)
             if (name == nbx_variant_name(v)) forced_variant = v;
         std::cout << "using block_size = " << want << std::endl;
