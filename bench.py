@@ -609,7 +609,8 @@ def main():
     tpath = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(wl_key)
+            tj = json.load(open(tpath))      # ncu-measured DRAM bytes per step, keyed by workload and kernel shape
+            traffic = tj.get(f"{wl_key}:{nbx.variant_names()[info1['variant']]}")
         except Exception:
             traffic = None
     ms_per_step = 1e3 * kernel_s / args.steps
@@ -636,7 +637,10 @@ def main():
                      "flop_per_pair": FLOP_PER_PAIR,
                      "hbm": {"algorithmic_bytes_per_launch": 64 * n // args.gpus, "achieved_gbs": round(64.0 * n / args.gpus / (kernel_s / args.steps) / 1e9, 2),
                              "peak_gbs": peaks.get("hbm_gbs"), "frac": round(64.0 * n / args.gpus / (kernel_s / args.steps) / 1e9 / peaks.get("hbm_gbs", 6650.0), 6)},
-                     "note": "compute-bound on the FP32 pipe, not HBM or tensor: 12 FP32 lane-ops per pair, 6 of them FMAs, so 20 algorithmic flop/pair caps at 20/24 = 83.3% of the FMA peak; HBM need is 64 B/body/step"},
+                     "note": ("compute-bound on the FP32 pipe, not HBM or tensor: q-scaled pair = 11 FP32 lane-ops per pair, 9 of them FMAs, so 20 algorithmic flop/pair caps at "
+                              "20/22 = 90.9% of the FMA peak (register-bank reads: 25 cycles where the pipe needs 22); HBM need is 64 B/body/step + 40 B/body for the record rewrite"
+                              if nbx.variant_names()[info1["variant"]].endswith("_qi") else
+                              "compute-bound on the FP32 pipe, not HBM or tensor: 12 FP32 lane-ops per pair, 6 of them FMAs, so 20 algorithmic flop/pair caps at 20/24 = 83.3% of the FMA peak; HBM need is 64 B/body/step")},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_detail": launches_detail, "parity": parity,
     }
     if strong and world > 1 and wl_key == "c3":

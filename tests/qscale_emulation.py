@@ -11,11 +11,11 @@ what that does to the force on sampled bodies at full N (sums in double, so that
 differs).   python tests/qscale_emulation.py [N] [uniform|plummer] [samples]
 
 Outcome (round 2): accuracy is no obstacle (N >= 65 536: both forms 1e-8 from fp64 per body; N = 2000: 2e-7
-instead of 2e-8), and the kernel built from it is correct (profiles/r02_qscaled_pair_experiment.{patch,log}:
-136 bounds-checked cases, C2 truth fixture 2.4e-7 / 8.9e-7) -- but it is 3-4 % SLOWER than the 12-instruction
-pair on the B200 (2600-2633 against 2706 G pairs/s at N = 1 M): the three subtract-FMAs read two 64-bit registers
-plus a 32-bit one each where the FADD2s read one plus one, and the FP32 pipe of this loop is bound by register
-operand reads, not by instruction count.  Not adopted; the patch is kept for the record.
+instead of 2e-8).  With the two j-bodies of a record in the packed lanes the kernel built from it was 3-4 % SLOWER
+than the 12-instruction pair (profiles/r02_qscaled_pair_experiment.{patch,log}): its three subtract-FMAs read two
+64-bit registers plus a 32-bit one, three registers from one bank.  With the two i-bodies of a record in the lanes
+the j data are scalars, the subtract-FMA reads a pair and two scalars of opposite register parity, and the kernel
+is 2.9 % FASTER at N = 1 M: that form is the default from 65 536 bodies on (nbx_kernels.cuh, the QS block).
 """
 import os
 import sys
