@@ -507,94 +507,101 @@ def main():
     # ---- parity of the headline workload on this set of GPUs
     parity = None if args.no_parity else B.parity(wl_key, ctx, host)
 
-    # ---- the three exchange modes, same workload, same box (N > 1)
     exchange_ab = None
-    if world > 1 and not args.no_extras:
-        exchange_ab = {}
-        ctx.close(); ctx = None
-        for name, mode in (("nccl", nbx.EXCHANGE_NCCL), ("nccl_overlap", nbx.EXCHANGE_NCCL_OVERLAP), ("p2p", nbx.EXCHANGE_P2P),
-                           ("p2p_unicast", nbx.EXCHANGE_P2P)):
-            c2 = B.make_ctx(wl_key, mode, multicast=0 if name == "p2p_unicast" else -1)
-            try:
-                B.upload(c2, host)
-                ks, _, _ = B.timed_steps(c2, 2, 1)
-                exchange_ab[name] = {"ms_per_step": round(1e3 * ks / 2, 3), "value": round(pairs_per_step * 2 / ks / 1e9, 1),
-                                     "used": XCH_NAMES[c2.exchange_used], "multicast": c2.multicast}
-            finally:
-                c2.close()
-
-        # the one-process form of the same run (nbx_run_group: the CLI's path; its multicast team needs no descriptor
-        # passing): rank 0 drives all the GPUs while the other ranks wait on a CPU barrier
-        gloo = torch.distributed.new_group(backend="gloo")
-        if rank == 0:
-            try:
-                ctxs = [nbx.Context(n, device=g, rank=g, world=world) for g in range(world)]
+    # Everything below is reporting around the headline (other exchange modes, the strong-scaling anchor, side workloads):
+    # a failure there must not cost the line that was just measured.
+    strong, also, extras_error = None, {}, None
+    try:
+        # ---- strong-scaling anchor: T1 on C3 (measured by the 1-GPU run; re-used by N > 1 runs on the same box)
+        if not args.no_extras:
+            if ctx is not None:
+                ctx.close(); ctx = None
+            try:       # the anchor is only valid for the GPU it was measured on (boxes share a hostname, GPUs differ by ~1.5 %)
+                box = socket.gethostname() + "/" + str(torch.cuda.get_device_properties(0).uuid)
+            except Exception:
+                box = socket.gethostname()
+            if world == 1:
+                blk = B.side_workload("c3", 3, 1)
+                strong = {"workload": WORKLOADS["c3"]["name"], "ms_per_step": blk["ms_per_step"], "value": blk["value"], "steps": 3,
+                          "frac_fp32_peak": blk["frac_fp32_peak"], "parity": blk["parity"], "box": box}
                 try:
-                    nbx.p2p_attach_group(ctxs)
-                    nbx.upload_group(ctxs, *host)
-                    nbx.run_group(ctxs, 1)
-                    ks = sum(nbx.run_group(ctxs, 1)[1] for _ in range(2))
-                    exchange_ab["p2p_one_process"] = {"ms_per_step": round(1e3 * ks / 2, 3), "value": round(pairs_per_step * 2 / ks / 1e9, 1),
-                                                      "multicast": bool(ctxs[0].info()["multicast"]),
-                                                      "what": "nbx_run_group from rank 0's process over all GPUs; multicast = the epilogue exchange is one "
-                                                              "multimem.st per record through a cuMulticast mapping instead of world-1 NVLink stores"}
+                    os.makedirs(os.path.dirname(ANCHOR_CACHE), exist_ok=True)
+                    with open(ANCHOR_CACHE, "w") as f:
+                        json.dump(strong, f)
+                except OSError:
+                    pass
+                also["c1"] = B.side_workload("c1", 5, 2, chunk=500)
+                also["c0"] = B.side_workload("c0", 5, 2, chunk=500)
+            elif wl_key == "c3":
+                anchor = None
+                if os.path.exists(ANCHOR_CACHE):
+                    try:
+                        a = json.load(open(ANCHOR_CACHE))
+                        if a.get("box") == box and time.time() - os.path.getmtime(ANCHOR_CACHE) < 6 * 3600:
+                            anchor = dict(a, source="the --gpus 1 run on this box (cached in " + ANCHOR_CACHE + ")")
+                    except Exception:
+                        anchor = None
+                if anchor is None:
+                    # no 1-GPU run on this box yet: rank 0 times C3 alone (1 warm-up + 2 steps) while the other GPUs idle
+                    t1 = [0.0]
+                    if rank == 0:
+                        with nbx.Context(n, device=B.local_rank) as c1:
+                            c1.upload(*host)
+                            c1.run(1)
+                            s = 0.0
+                            for _ in range(2):
+                                B.flush.zero_(); torch.cuda.synchronize()
+                                s += c1.run(1)[1]
+                            t1[0] = 1e3 * s / 2
+                    dist.barrier()
+                    ms1 = dist.reduce_scalar(t1[0], "max")
+                    anchor = {"workload": WORKLOADS["c3"]["name"], "ms_per_step": round(ms1, 4), "value": round(pairs_per_step / ms1 / 1e6, 2),
+                              "steps": 2, "box": box, "source": "timed inside this run on rank 0's GPU alone"}
+                strong = anchor
+            if world == 8:
+                also["c4"] = B.side_workload("c4", 2, 1)
+
+        # ---- the exchange modes, same workload, same box (N > 1)
+        if world > 1 and not args.no_extras:
+            exchange_ab = {}
+            if ctx is not None:
+                ctx.close(); ctx = None
+            for name, mode in (("p2p", nbx.EXCHANGE_P2P), ("p2p_unicast", nbx.EXCHANGE_P2P), ("nccl", nbx.EXCHANGE_NCCL),
+                               ("nccl_overlap", nbx.EXCHANGE_NCCL_OVERLAP)):
+                c2 = B.make_ctx(wl_key, mode, multicast=0 if name == "p2p_unicast" else -1)
+                try:
+                    B.upload(c2, host)
+                    ks, _, _ = B.timed_steps(c2, 2, 1)
+                    exchange_ab[name] = {"ms_per_step": round(1e3 * ks / 2, 3), "value": round(pairs_per_step * 2 / ks / 1e9, 1),
+                                         "used": XCH_NAMES[c2.exchange_used], "multicast": c2.multicast}
                 finally:
-                    for c in ctxs:
-                        c.close()
-            except Exception as ex:
-                exchange_ab["p2p_one_process"] = {"error": repr(ex)}
-        torch.distributed.barrier(group=gloo)
+                    c2.close()
 
-    # ---- strong-scaling anchor: T1 on C3 (measured by the 1-GPU run; re-used by N > 1 runs on the same box)
-    strong = None
-    also = {}
-    if not args.no_extras:
-        if ctx is not None:
-            ctx.close(); ctx = None
-        try:       # the anchor is only valid for the GPU it was measured on (boxes share a hostname, GPUs differ by ~1.5 %)
-            box = socket.gethostname() + "/" + str(torch.cuda.get_device_properties(0).uuid)
-        except Exception:
-            box = socket.gethostname()
-        if world == 1:
-            blk = B.side_workload("c3", 3, 1)
-            strong = {"workload": WORKLOADS["c3"]["name"], "ms_per_step": blk["ms_per_step"], "value": blk["value"], "steps": 3,
-                      "frac_fp32_peak": blk["frac_fp32_peak"], "parity": blk["parity"], "box": box}
-            try:
-                os.makedirs(os.path.dirname(ANCHOR_CACHE), exist_ok=True)
-                with open(ANCHOR_CACHE, "w") as f:
-                    json.dump(strong, f)
-            except OSError:
-                pass
-            also["c1"] = B.side_workload("c1", 5, 2, chunk=500)
-            also["c0"] = B.side_workload("c0", 5, 2, chunk=500)
-        elif wl_key == "c3":
-            anchor = None
-            if os.path.exists(ANCHOR_CACHE):
+            # the one-process form of the same run (nbx_run_group: the CLI's path; its multicast team needs no descriptor
+            # passing): rank 0 drives all the GPUs while the other ranks wait on a CPU barrier
+            gloo = torch.distributed.new_group(backend="gloo")
+            if rank == 0:
                 try:
-                    a = json.load(open(ANCHOR_CACHE))
-                    if a.get("box") == box and time.time() - os.path.getmtime(ANCHOR_CACHE) < 6 * 3600:
-                        anchor = dict(a, source="the --gpus 1 run on this box (cached in " + ANCHOR_CACHE + ")")
-                except Exception:
-                    anchor = None
-            if anchor is None:
-                # no 1-GPU run on this box yet: rank 0 times C3 alone (1 warm-up + 2 steps) while the other GPUs idle
-                t1 = [0.0]
-                if rank == 0:
-                    with nbx.Context(n, device=B.local_rank) as c1:
-                        c1.upload(*host)
-                        c1.run(1)
-                        s = 0.0
-                        for _ in range(2):
-                            B.flush.zero_(); torch.cuda.synchronize()
-                            s += c1.run(1)[1]
-                        t1[0] = 1e3 * s / 2
-                dist.barrier()
-                ms1 = dist.reduce_scalar(t1[0], "max")
-                anchor = {"workload": WORKLOADS["c3"]["name"], "ms_per_step": round(ms1, 4), "value": round(pairs_per_step / ms1 / 1e6, 2),
-                          "steps": 2, "box": box, "source": "timed inside this run on rank 0's GPU alone"}
-            strong = anchor
-        if world == 8:
-            also["c4"] = B.side_workload("c4", 2, 1)
+                    ctxs = [nbx.Context(n, device=g, rank=g, world=world) for g in range(world)]
+                    try:
+                        nbx.p2p_attach_group(ctxs)
+                        nbx.upload_group(ctxs, *host)
+                        nbx.run_group(ctxs, 1)
+                        ks = sum(nbx.run_group(ctxs, 1)[1] for _ in range(2))
+                        exchange_ab["p2p_one_process"] = {"ms_per_step": round(1e3 * ks / 2, 3), "value": round(pairs_per_step * 2 / ks / 1e9, 1),
+                                                          "multicast": bool(ctxs[0].info()["multicast"]),
+                                                          "what": "nbx_run_group from rank 0's process over all GPUs; multicast = the epilogue exchange is one "
+                                                                  "multimem.st per record through a cuMulticast mapping instead of world-1 NVLink stores"}
+                    finally:
+                        for c in ctxs:
+                            c.close()
+                except Exception as ex:
+                    exchange_ab["p2p_one_process"] = {"error": repr(ex)}
+            torch.distributed.barrier(group=gloo)
+
+    except Exception as ex:
+        extras_error = repr(ex)
+        print(f"[bench] rank {rank}: extras failed: {extras_error}", file=sys.stderr, flush=True)
 
     if rank != 0:
         if ctx is not None:
@@ -649,6 +656,8 @@ def main():
         line["exchange_ab"] = exchange_ab
     if also:
         line["also"] = also
+    if extras_error:
+        line["extras_error"] = extras_error
     if args.gpus == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline_block()
