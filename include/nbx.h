@@ -80,7 +80,7 @@ typedef struct nbx_info {
     int exchange;           /* NBX_EXCHANGE_*                                         */
     int variant;            /* kernel-shape index in use (after auto-selection)       */
     long long kernel_launches;   /* force-kernel launches since create                */
-    long long aux_launches;      /* pack/unpack/other launches since create           */
+    long long aux_launches;      /* pack/unpack launches, and the per-step record rewrite of the q-scaled shapes */
     double last_run_seconds;     /* device time of the last nbx_run (CUDA events)     */
     double kernel_seconds_total; /* device time summed over every nbx_run             */
     int device_error;       /* last device error word (0 = none): low byte 1 = peer timeout
