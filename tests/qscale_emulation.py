@@ -38,10 +38,8 @@ def rsqrt(x):
     return (1.0 / np.sqrt(x.astype(f64))).astype(f32)
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-    ic = sys.argv[2] if len(sys.argv) > 2 else "uniform"
-    ns = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+def errors(n, ic="uniform", ns=256):
+    """Relative force error against fp64 of the two formulations on `ns` sampled bodies: (current, q-scaled)."""
     from oracle import oracle as O
     if ic == "uniform":
         s = O.ic_uniform(n)
@@ -81,8 +79,15 @@ def main():
         tn = np.linalg.norm(t)
         err_cur.append(np.linalg.norm(c - t) / tn)
         err_new.append(np.linalg.norm(nw - t) / tn)
+    return np.array(err_cur), np.array(err_new)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+    ic = sys.argv[2] if len(sys.argv) > 2 else "uniform"
+    ns = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+    err_cur, err_new = errors(n, ic, ns)
     for name, e in (("current", err_cur), ("q-scaled", err_new)):
-        e = np.array(e)
         print(f"N={n} {ic:8s} {name:9s} force error vs fp64 over {ns} bodies: median {np.median(e):.2e}  p90 {np.quantile(e, .9):.2e}  max {e.max():.2e}")
 
 

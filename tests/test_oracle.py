@@ -217,3 +217,13 @@ def test_truth_fixture_is_reproducible(oracle):
     s = s0.copy()
     ke32 = oracle.run(s, int(tr["steps"]), variant="ver2")
     assert np.max(np.abs(ke32 - tr["ke"]) / tr["ke"]) < 5e-6
+
+
+def test_qscaled_pair_rounding_emulation():
+    """The arithmetic of the q-scaled pair (the kernel's default from 65 536 bodies on), emulated in numpy with one rounding
+    per FP32 instruction: its extra rounding of q*r_j costs a factor ~10 at N = 2000 and nothing once the sum is long."""
+    import qscale_emulation as Q
+    cur, new = Q.errors(2000, "uniform", 48)
+    assert np.all(np.isfinite(new)) and np.median(cur) < 1e-7 and np.median(new) < 1e-6 and new.max() < 1e-5
+    cur, new = Q.errors(65536, "uniform", 12)
+    assert np.median(new) < 1e-7 and new.max() < 1e-6
