@@ -99,6 +99,50 @@ def test_cli_multi_gpu(pkg, nbx):
 
 
 @pytest.mark.parametrize("exchange", ["nccl", "p2p", "nccl_overlap"])
+def test_qscaled_shape_in_every_exchange_mode(nbx, exchange):
+    """The q-scaled shape (default from 65 536 bodies on) forced at a small N through the three exchange modes on two GPUs:
+    its record rewrite runs per launch window (own shard, then the gathered shards, in the overlap mode) and carries the
+    peer wait in P2P mode.  Same gates as the 12-instruction shape above.
+    (Written after the round's GPU budget was spent: the P2P form of this path is what the 2-GPU default-plan tests and
+    bench line exercised at N = 262 144 ... 4 M; the two NCCL forms at this size have not run on hardware yet.)"""
+    world = 2
+    if _ngpu(nbx) < world:
+        pytest.skip(f"needs {world} GPUs")
+    qi = nbx.variant_names().index("r4_t256_u4_stage_f2_qi")
+    n, steps, splits = 6144, 6, 3
+    arrs = nbx.ic(n)
+    with nbx.Context(n) as c:
+        c.set_option("variant", qi); c.set_option("j_splits", splits); c.set_option("graph", 0)
+        c.upload(*arrs)
+        ke1, _ = c.run(steps)
+        st1 = c.state()
+    ctxs = [nbx.Context(n, device=g, rank=g, world=world) for g in range(world)]
+    try:
+        for c in ctxs:
+            c.set_option("variant", qi); c.set_option("j_splits", splits); c.set_option("exchange", XCH[exchange])
+        if exchange != "p2p":
+            nbx.comm_init_all(ctxs)
+        for c in ctxs:
+            c.upload(*arrs)
+        ke, _ = nbx.run_group(ctxs, steps)
+        out = [np.zeros(n, dtype=np.float32) for _ in range(6)]
+        for c in ctxs:
+            c.download(*out)
+        assert all(c.info()["aux_launches"] >= steps for c in ctxs)
+        if exchange == "nccl_overlap":
+            for a, b in zip(out, st1):
+                assert np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64)) < 1e-6
+            assert np.max(np.abs(ke - ke1) / ke1) < 1e-6
+        else:
+            for a, b in zip(out, st1):
+                assert np.array_equal(a, b)
+            assert np.max(np.abs(ke - ke1) / ke1) < 1e-12
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "p2p", "nccl_overlap"])
 def test_torchrun_two_ranks(nbx, exchange, tmp_path):
     """One process per GPU, the way bench.py is launched: ranks step together and agree with
     the single-GPU result."""
