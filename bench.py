@@ -573,7 +573,8 @@ def main():
                     B.upload(c2, host)
                     ks, _, _ = B.timed_steps(c2, 2, 1)
                     exchange_ab[name] = {"ms_per_step": round(1e3 * ks / 2, 3), "value": round(pairs_per_step * 2 / ks / 1e9, 1),
-                                         "used": XCH_NAMES[c2.exchange_used], "multicast": c2.multicast}
+                                         "used": XCH_NAMES[c2.exchange_used], "multicast": c2.multicast,
+                                         "kernel_shape": nbx.variant_names()[c2.info()["variant"]]}
                 finally:
                     c2.close()
 

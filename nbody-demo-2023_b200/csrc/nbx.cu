@@ -294,11 +294,14 @@ static Plan make_plan(int n_pad, int i_count, int world, int sm_count, int excha
                       int opt_accurate, int opt_splits, int opt_graph)
 {
     Plan p{};
+    const bool overlap = world > 1 && exchange == NBX_EXCHANGE_NCCL_OVERLAP;
+    // The q-scaled shape is not picked by itself in the NCCL-overlap mode (a step is two launches there, each with its own
+    // record rewrite: that combination has only been run with the shape forced through the "variant" option).
     p.variant = opt_variant >= 0 ? opt_variant
                 : opt_accurate   ? kAccurateVariant
                 : i_count < kSmallShardBodies ? kSmallVariant
-                : n_pad >= kQScaleMinBodies   ? kQScaleVariant
-                                              : kLargeVariant;
+                : (n_pad >= kQScaleMinBodies && !overlap) ? kQScaleVariant
+                                                          : kLargeVariant;
     const Variant &v = variants()[p.variant];
     const int bi = v.threads * v.r2 * 2;
     p.i_tiles = (i_count + bi - 1) / bi;
@@ -313,7 +316,6 @@ static Plan make_plan(int n_pad, int i_count, int world, int sm_count, int excha
     int splits = opt_splits;
     p.whole_tiles = 0;
     p.s_local = p.s_remote = 1;
-    const bool overlap = world > 1 && exchange == NBX_EXCHANGE_NCCL_OVERLAP;
     if (overlap) {
         // a step is two launches: the own j-shard (no remote data needed), then the other shards
         // once their all-gather has landed; every tile is split, partials of both launches meet

@@ -160,6 +160,9 @@ def test_launch_plan_host_logic(nbx):
     assert c1["use_graph"] == 1
     c2 = nbx.plan(1 << 20)
     assert names[c2["variant"]] == "r4_t256_u4_stage_f2_qi" and names[nbx.plan(65536)["variant"]] == "r4_t256_u4_stage_f2_qi"
+    # ... but not by itself in the NCCL-overlap mode (two launches per step)
+    assert names[nbx.plan(1 << 22, rank=3, world=8, exchange=2)["variant"]] == "r4_t256_u4_stage_f2"
+    assert names[nbx.plan(1 << 22, rank=3, world=8, exchange=1)["variant"]] == "r4_t256_u4_stage_f2_qi"
     assert (c2["i_tiles"], c2["whole_tiles"]) == (1024, 888) and c2["j_splits"] >= 13 and c2["use_graph"] == 0
     mid = nbx.plan(262144)                       # 256 tiles = 1.7 SM rounds: no unsplit tiles
     assert mid["whole_tiles"] == 0 and mid["j_splits"] > 1
