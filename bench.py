@@ -8,7 +8,8 @@ the O(N^2) force + Euler + kinetic-energy step (BASELINE.json), one JSON line on
 Headline workload (BASELINE.json configs): N GPUs = 1 -> C2, N = 1,048,576 uniform cube (the
 single-GPU FP32-roofline headline); N GPUs > 1 -> C3, N = 4,194,304 Plummer sphere, i-sharded
 STRONG scaling.  A "step" is one full time step: N^2 pair evaluations, the Euler update and the
-kinetic-energy reduction, fused in one kernel launch per GPU.
+kinetic-energy reduction, fused in one kernel launch per GPU -- preceded, from 65 536 bodies on, by the 10 us
+launch that rewrites the j-records for the q-scaled pair (`gpu_launches_detail` counts both).
 
 Besides the headline the line carries (all outside the headline's timed region):
   parity        correctness of what was just timed: kinetic energies and sampled positions against the
@@ -18,7 +19,8 @@ Besides the headline the line carries (all outside the headline's timed region):
   strong_anchor (--gpus 1) C3 timed on this one GPU: T1 of the strong-scaling curve; N > 1 lines report
                 strong_efficiency = T1 / (N * T_N) with T1 taken from the same box
   also          (--gpus 1) C1 and C0, the small-N configs; (--gpus 8) C4, the 16 M weak-scaling config
-  exchange_ab   (N > 1) the three position-exchange modes on the headline workload, 2 steps each
+  exchange_ab   (N > 1) the position-exchange modes on the headline workload, 2 steps each (each entry names its kernel shape)
+  extras_error  only if one of the blocks above failed: the headline, e2e and parity were measured before them and stand
   gpu_reference (--gpus 1) the reference's own CUDA backend on the same GPU, kernel-only and end-to-end,
                 with this build timed at the same N beside it
 
